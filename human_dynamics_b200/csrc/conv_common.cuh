@@ -1,0 +1,57 @@
+// Device-side parameter block shared by the SIMT and tcgen05 implicit-GEMM kernels.
+#pragma once
+#include "common.cuh"
+
+namespace hd {
+
+struct ConvParams {
+  const float *in; long long in_ld;
+  int n_img, H, W, Cin, Ho, Wo, KH, KW, stride, pad_t, pad_l;
+  const float *w_kn; int Cout; int K; int M;
+  const float *pre_scale, *pre_shift; int pre_img_stride, pre_relu;
+  const float *post_scale, *post_shift; int post_relu;
+  const float *res; long long res_ld; int res_H, res_W, res_stride;
+  float *out; long long out_ld;
+  int vec_out;   // out/res/post vectors allow float4 access
+  int K_pad;     // tensor-core path: padded K of the packed weights
+};
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
+  if (!d || !d->in || !d->out) { set_last_error_text("hd_conv_gemm: null in/out"); return HD_ERR_INVALID; }
+  if (d->n_img <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0 ||
+      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || d->in_ld < d->Cin || d->out_ld < d->Cout) {
+    set_last_error_text("hd_conv_gemm: bad shape");
+    return HD_ERR_INVALID;
+  }
+  if ((d->pre_scale == nullptr) != (d->pre_shift == nullptr)) {
+    set_last_error_text("hd_conv_gemm: pre_scale and pre_shift must be given together");
+    return HD_ERR_INVALID;
+  }
+  if (d->res && (d->res_ld < d->Cout || d->res_H <= 0 || d->res_W <= 0 || d->res_stride <= 0)) {
+    set_last_error_text("hd_conv_gemm: bad residual geometry");
+    return HD_ERR_INVALID;
+  }
+  p.in = d->in; p.in_ld = d->in_ld;
+  p.n_img = d->n_img; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.KH = d->KH; p.KW = d->KW; p.stride = d->stride; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.w_kn = d->w_kn; p.Cout = d->Cout; p.K = d->KH * d->KW * d->Cin;
+  const long long M = (long long)d->n_img * d->Ho * d->Wo;
+  if (M > 0x7fffffffLL) { set_last_error_text("hd_conv_gemm: M overflows int32"); return HD_ERR_INVALID; }
+  p.M = (int)M;
+  p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.pre_img_stride = d->pre_img_stride; p.pre_relu = d->pre_relu;
+  p.post_scale = d->post_scale; p.post_shift = d->post_shift; p.post_relu = d->post_relu;
+  p.res = d->res; p.res_ld = d->res_ld; p.res_H = d->res_H; p.res_W = d->res_W; p.res_stride = d->res_stride;
+  p.out = d->out; p.out_ld = d->out_ld;
+  p.vec_out = (d->Cout % 4 == 0) && (d->out_ld % 4 == 0) && aligned16(d->out) &&
+              (!d->res || ((d->res_ld % 4 == 0) && aligned16(d->res))) &&
+              (!d->post_scale || aligned16(d->post_scale)) && (!d->post_shift || aligned16(d->post_shift));
+  p.K_pad = d->K_pad;
+  return HD_OK;
+}
+
+int launch_conv_simt(const ConvParams &p, cudaStream_t st);
+int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st);
+
+}  // namespace hd

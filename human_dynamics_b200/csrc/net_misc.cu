@@ -1,0 +1,137 @@
+// Small non-GEMM pieces of the network path: ResNet root/tail, GroupNorm statistics, IEF glue.
+#include "conv_common.cuh"
+
+namespace {
+
+// pool1 (slim.max_pool2d 3x3/2 'SAME'): padded cells are ignored.
+__global__ void maxpool3x3s2_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4,
+                                    int Ho, int Wo, int pt, int pl) {
+  const long long total = (long long)N * Ho * Wo * C4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C4);
+  long long r = i / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - pt + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - pl + kx;
+      if (ix < 0 || ix >= W) continue;
+      const float4 v = __ldg(in + ((size_t)((size_t)n * H + iy) * W + ix) * C4 + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  out[i] = m;
+}
+
+// postnorm BN + ReLU + mean over HW.  One thread per (n, c); consecutive threads -> consecutive channels.
+__global__ void bnrelu_avgpool_kernel(const float *__restrict__ in, const float *__restrict__ scale,
+                                      const float *__restrict__ shift, float *__restrict__ out, int N, int HW, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C) return;
+  const int c = (int)(i % C);
+  const long long n = i / C;
+  const float s = __ldg(scale + c), b = __ldg(shift + c);
+  const float *p = in + (size_t)n * HW * C + c;
+  float acc = 0.f;
+  for (int k = 0; k < HW; ++k) acc += fmaxf(__ldg(p + (size_t)k * C) * s + b, 0.f);
+  out[i] = acc / (float)HW;
+}
+
+// One warp per (clip, group): two-pass mean / biased variance over T x (C/groups) elements, then the
+// per-channel affine that the conv prologue applies: y = x*gain + offset.
+__global__ void __launch_bounds__(128) groupnorm_stats_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                              const float *__restrict__ beta, float *__restrict__ gain,
+                                                              float *__restrict__ offset, int B, int T, int C, int groups,
+                                                              float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wg >= B * groups) return;
+  const int b = wg / groups, g = wg % groups;
+  const int cg = C / groups;
+  const float *base = x + (size_t)b * T * C + (size_t)g * cg;
+  const int cnt = T * cg;
+  float s = 0.f;
+  for (int i = lane; i < cnt; i += 32) s += __ldg(base + (size_t)(i / cg) * C + (i % cg));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)cnt;
+  float v = 0.f;
+  for (int i = lane; i < cnt; i += 32) {
+    const float d = __ldg(base + (size_t)(i / cg) * C + (i % cg)) - mean;
+    v += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)cnt + eps);
+  for (int c = lane; c < cg; c += 32) {
+    const int ch = g * cg + c;
+    const float gn = rstd * __ldg(gamma + ch);
+    gain[(size_t)b * C + ch] = gn;
+    offset[(size_t)b * C + ch] = __ldg(beta + ch) - mean * gn;
+  }
+}
+
+__global__ void ief_delta_init_kernel(const float *__restrict__ theta, float *__restrict__ dst, int dst_ld, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 85) return;
+  const int c = i % 85, n = i / 85;
+  dst[(size_t)n * dst_ld + c] = c == 0 ? 1.0f : (c < 3 ? 0.0f : theta[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *out, int N, int H, int W, void *stream) {
+  HD_REQUIRE(in && w && bias && out && N > 0 && H > 0 && W > 0 && (H % 2 == 0) && (W % 2 == 0), "hd_conv1_7x7s2: bad arguments");
+  hd_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.in = in; d.in_ld = 3; d.n_img = N; d.H = H; d.W = W; d.Cin = 3;
+  d.Ho = H / 2; d.Wo = W / 2; d.KH = 7; d.KW = 7; d.stride = 2; d.pad_t = 3; d.pad_l = 3;   // conv2d_same: explicit pad 3+3
+  d.w_kn = w; d.Cout = 64; d.post_shift = bias; d.out = out; d.out_ld = 64; d.impl = HD_IMPL_SIMT;
+  hd::ConvParams p;
+  int rc = hd::fill_params(&d, p);
+  if (rc) return rc;
+  return hd::launch_conv_simt(p, (cudaStream_t)stream);
+}
+
+int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, void *stream) {
+  HD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hd_maxpool3x3s2_same: bad arguments");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int pth = (Ho - 1) * 2 + 3 - H, ptw = (Wo - 1) * 2 + 3 - W;
+  const int pt = (pth > 0 ? pth : 0) / 2, pl = (ptw > 0 ? ptw : 0) / 2;
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  maxpool3x3s2_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N, H, W, C / 4, Ho, Wo, pt, pl);
+  return hd::check_launch("maxpool3x3s2_kernel");
+}
+
+int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, float *out, int N, int HW, int C, void *stream) {
+  HD_REQUIRE(in && scale && shift && out && N > 0 && HW > 0 && C > 0, "hd_bnrelu_avgpool: bad arguments");
+  bnrelu_avgpool_kernel<<<hd::ceil_div((long long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(in, scale, shift, out, N, HW, C);
+  return hd::check_launch("bnrelu_avgpool_kernel");
+}
+
+int hd_groupnorm_stats(const float *x, const float *gamma, const float *beta, float *gain, float *offset, int B, int T,
+                       int C, int groups, float eps, void *stream) {
+  HD_REQUIRE(x && gamma && beta && gain && offset && B > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0,
+             "hd_groupnorm_stats: bad arguments");
+  groupnorm_stats_kernel<<<hd::ceil_div((long long)B * groups, 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, gain, offset,
+                                                                                                 B, T, C, groups, eps);
+  return hd::check_launch("groupnorm_stats_kernel");
+}
+
+int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *stream) {
+  HD_REQUIRE(theta && dst && N > 0 && dst_ld >= 85, "hd_ief_delta_init: bad arguments");
+  ief_delta_init_kernel<<<hd::ceil_div((long long)N * 85, 256), 256, 0, (cudaStream_t)stream>>>(theta, dst, dst_ld, N);
+  return hd::check_launch("ief_delta_init_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""HMMR inference engine: the wiring of Tester.build_test_model (src/evaluation/tester.py:169-215) over the
+B200 kernels -- images -> ResNet-v2-50 -> f_movie -> IEF (main + delta heads) -> SMPL -> projection.
+
+All compute goes through libhd_b200.so on the current CUDA stream; torch is used for device buffers,
+streams and host<->device copies only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import HMMRConfig
+from .nets import (FMoviePlan, IEFPlan, PackedConv, PackedFMovie, PackedIEF, PackedResNet, ResNetPlan, _dev)
+from .smpl import SMPLConstants
+from ._lib import lib, current_stream
+
+
+def load_weights(path_or_dict):
+    """TF-named variable dict from an in-memory dict or an .npz (a TF checkpoint must be converted offline)."""
+    if isinstance(path_or_dict, dict):
+        return path_or_dict
+    if isinstance(path_or_dict, str) and path_or_dict.endswith('.npz'):
+        with np.load(path_or_dict) as z:
+            return {k: z[k] for k in z.files}
+    raise ValueError('weights must be a dict of TF-named arrays or a .npz path (got %r)' % (path_or_dict,))
+
+
+class PackedHal(object):
+    """fc2_res hallucinator (models.py:270-296)."""
+
+    def __init__(self, w, device, tc=False, name='fc2_res'):
+        self.fc1 = PackedConv(w[name + '/fc1/weights'], device, post_shift=w[name + '/fc1/biases'], post_relu=True, tc=tc)
+        self.fc2 = PackedConv(w[name + '/fc2/weights'], device, post_shift=w[name + '/fc2/biases'], post_relu=True, tc=tc)
+        self.fc3 = PackedConv(w[name + '/fc3/weights'], device, post_shift=w[name + '/fc3/biases'], tc=tc)
+
+
+class HMMREngine(object):
+    def __init__(self, weights, smpl_model, config: HMMRConfig | None = None, device=None, impl=None):
+        if not torch.cuda.is_available():
+            raise _lib.HDError('HMMREngine needs a CUDA device: the hot path has no CPU fallback')
+        self.config = config or HMMRConfig()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.impl = impl or self.config.impl
+        tc = self.impl in ('auto', 'tc3', 'tc1')
+        w = load_weights(weights)
+        self.delta_t_values = [int(d) for d in self.config.delta_t_values]
+        with torch.cuda.device(self.device):
+            self.resnet = PackedResNet(w, self.device, tc=tc)
+            self.fmovie = PackedFMovie(w, self.device, self.config.num_conv_layers, tc=tc) \
+                if any(k.startswith('AZ_FC_block2_conv1') for k in w) else None
+            self.ief = PackedIEF(w, self.device, delta_t_values=self.delta_t_values, tc=tc)
+            self.hal = PackedHal(w, self.device, tc=tc) if 'fc2_res/fc1/weights' in w else None
+            self.smpl = smpl_model if isinstance(smpl_model, SMPLConstants) else SMPLConstants(smpl_model, device=self.device)
+        self._resnet_plans = {}
+        self._fmovie_plans = {}
+        self._ief_plans = {}
+        self._hal_plans = {}
+        self._theta0 = {}
+        self._phi = {}
+        self._outs = {}
+
+    # ---------------------------------------------------------------- stage API
+    def _resnet_plan(self, n, size):
+        key = (n, size)
+        if key not in self._resnet_plans:
+            self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl)
+        return self._resnet_plans[key]
+
+    def encode_images(self, images, out=None):
+        """encoder_resnet: (N,H,W,3) float32 CUDA NHWC -> (N,2048).  Processes `frame_chunk` frames per pass."""
+        if not images.is_cuda or images.dtype != torch.float32:
+            raise _lib.HDError('encode_images: float32 CUDA tensor required (no CPU fallback exists)')
+        if images.dim() != 4 or images.shape[3] != 3 or images.shape[1] != images.shape[2]:
+            raise _lib.HDError('encode_images: expected (N,S,S,3) NHWC, got %s' % (tuple(images.shape),))
+        images = images.contiguous()
+        N, size = images.shape[0], images.shape[1]
+        phi = out if out is not None else torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=images.device)
+        chunk = max(1, min(int(self.config.frame_chunk), N)) if N else 1
+        st = current_stream()
+        for i in range(0, N, chunk):
+            n = min(chunk, N - i)
+            self._resnet_plan(n, size).run(images[i:i + n], phi[i:i + n], st)
+        return phi
+
+    def temporal_encode(self, feats):
+        """az_fc2_groupnorm ("f_movie"): (B,T,2048) -> (B,T,2048)."""
+        if self.fmovie is None:
+            raise _lib.HDError('no f_movie weights were loaded')
+        B, T = feats.shape[0], feats.shape[1]
+        key = (B, T)
+        if key not in self._fmovie_plans:
+            self._fmovie_plans[key] = FMoviePlan(self.fmovie, B, T, self.impl)
+        return self._fmovie_plans[key].run(feats.contiguous())
+
+    def hallucinate(self, feats):
+        """fc2_res: (B,T,2048) -> (B,T,2048)   (pred_mode='hal')."""
+        if self.hal is None:
+            raise _lib.HDError('no fc2_res weights were loaded')
+        feats = feats.contiguous()
+        N = feats.shape[0] * feats.shape[1]
+        if N not in self._hal_plans:
+            f32 = dict(dtype=torch.float32, device=feats.device)
+            self._hal_plans[N] = [torch.empty((N, 2048), **f32) for _ in range(3)]
+        h1, h2, out = self._hal_plans[N]
+        st = current_stream()
+        self.hal.fc1.bind(feats, N, 1, 1, h1, impl=self.impl).run(st)
+        self.hal.fc2.bind(h1, N, 1, 1, h2, impl=self.impl).run(st)
+        self.hal.fc3.bind(h2, N, 1, 1, out, res=feats, res_geom=(2048, 1, 1, 1), impl=self.impl).run(st)
+        return out.view(feats.shape)
+
+    def theta_mean(self, N):
+        if N not in self._theta0:
+            self._theta0[N] = self.ief.mean_param.expand(N, 85).contiguous()
+        return self._theta0[N]
+
+    def regress(self, feats, omega_start=None, delta_keys=None):
+        """call_hmr_ief: feats (N,2048) -> (omega (N,85), {dt: (N,85)})."""
+        feats = feats.contiguous()
+        N = feats.shape[0]
+        keys = tuple(sorted(self.ief.deltas.keys())) if delta_keys is None else tuple(sorted(k for k in delta_keys if k != 0))
+        plan = self._ief_plan(N, keys)
+        theta0 = self.theta_mean(N) if omega_start is None else omega_start.contiguous()
+        return plan.run(feats.view(N, -1), theta0)
+
+    def _ief_plan(self, N, keys):
+        pk = (N, tuple(keys))
+        if pk not in self._ief_plans:
+            self._ief_plans[pk] = IEFPlan(self.ief, N, self.config.num_stage, list(keys), self.impl)
+        return self._ief_plans[pk]
+
+    def _out_buffers(self, N, D):
+        key = (N, D)
+        if key not in self._outs:
+            V, K = self.smpl.num_verts, self.smpl.num_kps
+            f32 = dict(dtype=torch.float32, device=self.device)
+
+            def mk(rows):
+                return {'verts': torch.empty((rows, V, 3), **f32), 'joints': torch.empty((rows, K, 3), **f32),
+                        'Rs': torch.empty((rows, 24, 3, 3), **f32), 'Jtr': torch.empty((rows, 24, 3), **f32),
+                        'kps': torch.empty((rows, K, 2), **f32)}
+            self._outs[key] = (mk(N), mk(N * D) if D else None)
+        return self._outs[key]
+
+    # ---------------------------------------------------------------- full window
+    def predict(self, images, single_frame=False):
+        """Tester.predict on device.  images (B,T,S,S,3) float32 CUDA -> dict of CUDA tensors with the 14
+        fetch keys of tester.py:217-255 (+ '_phi', '_movie_strips' for inspection).  Outputs are plan-owned
+        buffers that the next predict() of the same shape overwrites."""
+        if images.dim() != 5:
+            raise _lib.HDError('predict: expected (B,T,S,S,3)')
+        B, T = images.shape[0], images.shape[1]
+        N = B * T
+        key = ('phi', N)
+        if key not in self._phi:
+            self._phi[key] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
+        phi = self.encode_images(images.reshape((N,) + tuple(images.shape[2:])), out=self._phi[key])
+        return self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
+
+    def predict_from_features(self, phi, single_frame=False):
+        B, T = phi.shape[0], phi.shape[1]
+        N = B * T
+        if single_frame:
+            strips = phi
+            omega, deltas = self.regress(phi.reshape(N, -1), delta_keys=())
+        else:
+            mode = self.config.pred_mode
+            if mode == 'pred':
+                strips = self.temporal_encode(phi)
+            elif mode == 'hal':
+                strips = self.hallucinate(phi)
+            else:
+                raise Exception('Pred mode {} not recognized'.format(mode))
+            omega, deltas = self.regress(strips.reshape(N, -1))
+        dts = sorted(deltas.keys())
+        D = len(dts)
+        K, V = self.smpl.num_kps, self.smpl.num_verts
+        o0, od = self._out_buffers(N, D)
+        cams = omega[:, 0:3]
+        # OmegasPred.compute_smpl (omega.py:263-304) for the dt=0 instance ...
+        self.smpl.forward(omega[:, 75:85], omega[:, 3:75], cam=cams, out=o0)
+        out = {'cams': cams.reshape(B, T, 3), 'joints': o0['joints'].view(B, T, K, 3), 'kps': o0['kps'].view(B, T, K, 2),
+               'poses': o0['Rs'].view(B, T, 24, 3, 3), 'shapes': omega[:, 75:85].reshape(B, T, 10),
+               'verts': o0['verts'].view(B, T, V, 3), 'omegas': omega.view(B, T, 85)}
+        if D:
+            # ... and every delta instance; cams come from the dt=0 prediction (set_cams, tester.py:210-213).
+            # Pose n of delta i is written to slot n*D+i, i.e. directly into the [B,T,D,...] stacking of tester.py:252.
+            for i, dt in enumerate(dts):
+                d = deltas[dt]
+                self.smpl.forward(d[:, 75:85], d[:, 3:75], cam=cams, out=od, slot=(D, i))
+            omegas_delta = self._ief_plan(N, tuple(dts)).delta_all.view(B, T, D, 85)
+            out.update({'cams_delta': cams.reshape(B, T, 1, 3).expand(B, T, D, 3),
+                        'joints_delta': od['joints'].view(B, T, D, K, 3), 'kps_delta': od['kps'].view(B, T, D, K, 2),
+                        'poses_delta': od['Rs'].view(B, T, D, 24, 3, 3), 'shapes_delta': omegas_delta[..., 75:85],
+                        'verts_delta': od['verts'].view(B, T, D, V, 3), 'omegas_delta': omegas_delta})
+        out['_phi'] = phi
+        out['_movie_strips'] = strips
+        return out
+
+    def num_launches(self, B, T, size=224, single_frame=False):
+        """Kernel launches of one predict() (for bench.py's gpu_launches claim; verified against hd_launch_count)."""
+        N = B * T
+        chunk = max(1, min(int(self.config.frame_chunk), N))
+        n = 0
+        for i in range(0, N, chunk):
+            n += self._resnet_plan(min(chunk, N - i), size).num_launches
+        return n

@@ -1,0 +1,400 @@
+"""Host-side layer plans for the three networks on the path: slim ResNet-v2-50, f_movie, IEF.
+
+A *plan* is a list of pre-filled C descriptors (hd_conv_desc) over pre-allocated device buffers, so a
+forward pass is a sequence of ctypes calls with no Python-side tensor math and no allocation.
+Weights come in as a dict of numpy arrays keyed by TF variable names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, fptr, current_stream, ConvDesc
+
+RESNET_BLOCKS = ((64, 3, 2), (128, 4, 2), (256, 6, 2), (512, 3, 1))
+BN_EPS = 1e-5        # resnet_arg_scope batch_norm_epsilon [TF-ext]
+GN_EPS = 1e-6        # tf.contrib.layers.group_norm epsilon [TF-ext]
+GN_GROUPS = 32
+
+
+def _dev(a, device, dtype=np.float32):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device)
+
+
+def fold_bn(w, prefix):
+    """BN inference -> (scale, shift): y = x*scale + shift  (A.5)."""
+    g = w[prefix + '/gamma'].astype(np.float64)
+    b = w[prefix + '/beta'].astype(np.float64)
+    m = w[prefix + '/moving_mean'].astype(np.float64)
+    v = w[prefix + '/moving_variance'].astype(np.float64)
+    s = g / np.sqrt(v + BN_EPS)
+    return s.astype(np.float32), (b - m * s).astype(np.float32)
+
+
+def tf32_split(w):
+    """w (float32) -> (hi, lo): hi has the low 13 mantissa bits cleared (what the tensor core reads), lo = w - hi."""
+    bits = w.view(np.uint32) & np.uint32(0xFFFFE000)
+    hi = bits.view(np.float32)
+    lo = (w - hi).astype(np.float32)
+    return hi, lo
+
+
+class PackedConv(object):
+    """Device-resident weights (+ epilogue vectors) of one conv / FC layer."""
+
+    def __init__(self, w_hwio, device, post_scale=None, post_shift=None, post_relu=False, stride=1, pad=(0, 0),
+                 tc=False):
+        w_hwio = np.asarray(w_hwio, np.float32)
+        if w_hwio.ndim == 2:
+            w_hwio = w_hwio[None, None]
+        self.KH, self.KW, self.Cin, self.Cout = w_hwio.shape
+        self.K = self.KH * self.KW * self.Cin
+        self.stride = stride
+        self.pad_t, self.pad_l = pad
+        self.device = device
+        w_kn = w_hwio.reshape(self.K, self.Cout)
+        self.w_kn = _dev(w_kn, device)
+        self.post_scale = _dev(post_scale, device) if post_scale is not None else None
+        self.post_shift = _dev(post_shift, device) if post_shift is not None else None
+        self.post_relu = bool(post_relu)
+        self.tc = False
+        self.K_pad = 0
+        if tc and self.Cin % 32 == 0:
+            self.K_pad = self.K
+            rows = (self.Cout + 127) // 128 * 128
+            w_nk = np.zeros((rows, self.K_pad), np.float32)
+            w_nk[:self.Cout] = w_kn.T
+            hi, lo = tf32_split(w_nk)
+            self.w_nk_hi = _dev(hi, device)
+            self.w_nk_lo = _dev(lo, device)
+            self.tmap_hi = (C.c_ubyte * 128)()
+            self.tmap_lo = (C.c_ubyte * 128)()
+            check(lib.hd_make_weight_tmap(fptr(self.w_nk_hi), rows, self.K_pad, 128, C.cast(self.tmap_hi, C.c_void_p)),
+                  'hd_make_weight_tmap')
+            check(lib.hd_make_weight_tmap(fptr(self.w_nk_lo), rows, self.K_pad, 128, C.cast(self.tmap_lo, C.c_void_p)),
+                  'hd_make_weight_tmap')
+            self.tc = True
+
+    def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto'):
+        """Fill a descriptor.  inp/out/res: CUDA float32 tensors (only their data_ptr is used).
+
+        pre = (scale, shift, img_stride, relu); res_geom = (res_ld, res_H, res_W, res_stride).
+        """
+        d = ConvDesc()
+        Ho = (H + 2 * self.pad_t - self.KH) // self.stride + 1 if self.KH > 1 else (H - 1) // self.stride + 1
+        Wo = (W + 2 * self.pad_l - self.KW) // self.stride + 1 if self.KW > 1 else (W - 1) // self.stride + 1
+        d.in_ = inp.data_ptr(); d.in_ld = self.Cin if in_ld is None else in_ld
+        d.n_img, d.H, d.W, d.Cin = n_img, H, W, self.Cin
+        d.Ho, d.Wo, d.KH, d.KW = Ho, Wo, self.KH, self.KW
+        d.stride, d.pad_t, d.pad_l = self.stride, self.pad_t, self.pad_l
+        d.w_kn = self.w_kn.data_ptr()
+        d.Cout = self.Cout
+        d.K_pad = self.K_pad
+        if pre is not None:
+            d.pre_scale, d.pre_shift = pre[0].data_ptr(), pre[1].data_ptr()
+            d.pre_img_stride, d.pre_relu = int(pre[2]), int(pre[3])
+        if self.post_scale is not None:
+            d.post_scale = self.post_scale.data_ptr()
+        if self.post_shift is not None:
+            d.post_shift = self.post_shift.data_ptr()
+        d.post_relu = int(self.post_relu)
+        if res is not None:
+            d.res = res.data_ptr()
+            if res_geom is None:
+                res_geom = (self.Cout, Ho, Wo, 1)
+            d.res_ld, d.res_H, d.res_W, d.res_stride = res_geom
+        d.out = out.data_ptr(); d.out_ld = self.Cout if out_ld is None else out_ld
+        use_tc = self.tc and impl in ('auto', 'tc3', 'tc1') and (d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)
+        if impl in ('tc3', 'tc1') and not use_tc:
+            use_tc = False           # ragged layers always run on the exact-FP32 SIMT kernel
+        if use_tc:
+            d.impl = _lib.HD_IMPL_TC_1XTF32 if impl == 'tc1' else _lib.HD_IMPL_TC_3XTF32
+            d.w_nk_hi, d.w_nk_lo = self.w_nk_hi.data_ptr(), self.w_nk_lo.data_ptr()
+            d.tmap_hi = C.cast(self.tmap_hi, C.c_void_p)
+            d.tmap_lo = C.cast(self.tmap_lo, C.c_void_p)
+        else:
+            d.impl = _lib.HD_IMPL_SIMT
+        return ConvOp(d, (self, inp, out, pre, res), (Ho, Wo))
+
+
+class ConvOp(object):
+    __slots__ = ('d', 'keep', 'out_hw', 'ref')
+
+    def __init__(self, d, keep, out_hw):
+        self.d, self.keep, self.out_hw = d, keep, out_hw
+        self.ref = C.byref(d)
+
+    def run(self, stream):
+        rc = lib.hd_conv_gemm(self.ref, stream)
+        if rc:
+            check(rc, 'hd_conv_gemm')
+
+
+# ------------------------------------------------------------------------------------------------
+# ResNet-v2-50 (slim)  -- src/models.py:50-77
+# ------------------------------------------------------------------------------------------------
+class PackedResNet(object):
+    def __init__(self, w, device, tc=False, blocks=RESNET_BLOCKS):
+        p = 'resnet_v2_50'
+        self.device = device
+        self.blocks = blocks
+        self.conv1_w = _dev(np.asarray(w[p + '/conv1/weights'], np.float32).reshape(147, 64), device)
+        self.conv1_b = _dev(w[p + '/conv1/biases'], device)
+        self.units = []
+        d_in = 64
+        for b, (base, units, bstride) in enumerate(blocks, start=1):
+            depth = 4 * base
+            for u in range(1, units + 1):
+                q = '%s/block%d/unit_%d/bottleneck_v2' % (p, b, u)
+                stride = bstride if u == units else 1
+                ps, pb = fold_bn(w, q + '/preact')
+                unit = {'stride': stride, 'base': base, 'depth': depth, 'd_in': d_in,
+                        'pre': (_dev(ps, device), _dev(pb, device))}
+                if d_in != depth:
+                    unit['shortcut'] = PackedConv(w[q + '/shortcut/weights'], device,
+                                                  post_shift=w[q + '/shortcut/biases'], stride=stride, tc=tc)
+                s1, b1 = fold_bn(w, q + '/conv1/BatchNorm')
+                unit['conv1'] = PackedConv(w[q + '/conv1/weights'], device, s1, b1, True, tc=tc)
+                s2, b2 = fold_bn(w, q + '/conv2/BatchNorm')
+                # conv2d_same: stride 1 -> SAME (pad 1); stride 2 -> explicit pad 1+1 then VALID  (A.2)
+                unit['conv2'] = PackedConv(w[q + '/conv2/weights'], device, s2, b2, True, stride=stride, pad=(1, 1), tc=tc)
+                unit['conv3'] = PackedConv(w[q + '/conv3/weights'], device, post_shift=w[q + '/conv3/biases'], tc=tc)
+                self.units.append(unit)
+                d_in = depth
+        s, b = fold_bn(w, p + '/postnorm')
+        self.post = (_dev(s, device), _dev(b, device))
+        self.out_dim = d_in
+
+
+class ResNetPlan(object):
+    """Forward plan for a fixed number of frames n (activation buffers are reused across chunks)."""
+
+    def __init__(self, packed: PackedResNet, n, size=224, impl='auto'):
+        self.p = packed
+        self.n = n
+        self.size = size
+        dev = packed.device
+        H1 = size // 2                        # conv1 output (explicit pad 3, stride 2)
+        H2 = (H1 + 1) // 2                    # pool1 SAME
+        big = n * H2 * H2 * 256               # also = n*H1*H1*64
+        self.bufA = torch.empty(big, dtype=torch.float32, device=dev)
+        self.bufB = torch.empty(big, dtype=torch.float32, device=dev)
+        self.bufS = torch.empty(max(big, n * H1 * H1 * 64), dtype=torch.float32, device=dev)
+        self.bufR1 = torch.empty(n * H2 * H2 * 64, dtype=torch.float32, device=dev)
+        self.bufR2 = torch.empty(n * H2 * H2 * 64, dtype=torch.float32, device=dev)
+        self.H1, self.H2 = H1, H2
+        self.ops = []
+        x, y = self.bufA, self.bufB
+        H = H2
+        for unit in packed.units:
+            s = unit['stride']
+            Ho = (H - 1) // s + 1
+            pre = (unit['pre'][0], unit['pre'][1], 0, 1)
+            if 'shortcut' in unit:
+                self.ops.append(unit['shortcut'].bind(x, n, H, H, self.bufS, pre=pre, impl=impl))
+                res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
+            else:
+                res, res_geom = x, (unit['depth'], H, H, s)      # identity, or max_pool2d(1x1, stride) = subsample
+            self.ops.append(unit['conv1'].bind(x, n, H, H, self.bufR1, pre=pre, impl=impl))
+            self.ops.append(unit['conv2'].bind(self.bufR1, n, H, H, self.bufR2, impl=impl))
+            self.ops.append(unit['conv3'].bind(self.bufR2, n, Ho, Ho, y, res=res, res_geom=res_geom, impl=impl))
+            x, y = y, x
+            H = Ho
+        self.final = x
+        self.final_hw = H * H
+
+    def run(self, images, out_phi, stream=None):
+        """images: (n,size,size,3) contiguous float32 CUDA view; out_phi: (n,2048) contiguous view."""
+        st = current_stream() if stream is None else stream
+        n, p = self.n, self.p
+        check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
+              'hd_conv1_7x7s2')
+        check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64, st), 'hd_maxpool3x3s2_same')
+        for op in self.ops:
+            op.run(st)
+        check(lib.hd_bnrelu_avgpool(fptr(self.final), fptr(p.post[0]), fptr(p.post[1]), fptr(out_phi), n, self.final_hw,
+                                    p.out_dim, st), 'hd_bnrelu_avgpool')
+
+    @property
+    def num_launches(self):
+        return 3 + len(self.ops)
+
+
+# ------------------------------------------------------------------------------------------------
+# f_movie temporal encoder -- src/models.py:121-228
+# ------------------------------------------------------------------------------------------------
+class PackedFMovie(object):
+    def __init__(self, w, device, num_conv_layers=3, tc=False):
+        self.device = device
+        self.blocks = []
+        for i in range(num_conv_layers):
+            name = 'block_%d' % i
+            blk = {}
+            for k in (1, 2):
+                blk['gn%d' % k] = (_dev(w['AZ_FC_block_preact_gn%d%s/gamma' % (k, name)], device),
+                                   _dev(w['AZ_FC_block_preact_gn%d%s/beta' % (k, name)], device))
+                blk['conv%d' % k] = PackedConv(w['AZ_FC_block2_conv%d%s/weights' % (k, name)], device,
+                                               post_shift=w['AZ_FC_block2_conv%d%s/biases' % (k, name)], pad=(1, 0), tc=tc)
+            self.blocks.append(blk)
+        self.C = self.blocks[0]['conv1'].Cin if self.blocks else 2048
+
+
+class FMoviePlan(object):
+    def __init__(self, packed: PackedFMovie, B, T, impl='auto'):
+        self.p, self.B, self.T = packed, B, T
+        dev, Cc = packed.device, packed.C
+        self.gain = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+        self.offset = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+        self.mid = torch.empty((B, T, Cc), dtype=torch.float32, device=dev)
+        self.bufs = [torch.empty((B, T, Cc), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.impl = impl
+        self._bound_for = None
+
+    def _bind(self, x):
+        steps = []
+        cur = x
+        pre = (self.gain, self.offset, self.p.C, 1)
+        B, T = self.B, self.T
+        for i, blk in enumerate(self.p.blocks):
+            out = self.bufs[i % 2]
+            steps.append(('gn', cur, blk['gn1']))
+            steps.append(('conv', blk['conv1'].bind(cur, B, T, 1, self.mid, pre=pre, impl=self.impl)))
+            steps.append(('gn', self.mid, blk['gn2']))
+            steps.append(('conv', blk['conv2'].bind(self.mid, B, T, 1, out, pre=pre, res=cur,
+                                                    res_geom=(self.p.C, T, 1, 1), impl=self.impl)))
+            cur = out
+        self.steps, self.out = steps, cur
+        self._bound_for = x.data_ptr()
+
+    def run(self, x, stream=None):
+        """x (B,T,C) contiguous float32 CUDA -> (B,T,C) (a plan-owned buffer; x itself if there are no blocks)."""
+        st = current_stream() if stream is None else stream
+        if self._bound_for != x.data_ptr():
+            self._bind(x)
+        for s in self.steps:
+            if s[0] == 'gn':
+                check(lib.hd_groupnorm_stats(fptr(s[1]), fptr(s[2][0]), fptr(s[2][1]), fptr(self.gain), fptr(self.offset),
+                                             self.B, self.T, self.p.C, GN_GROUPS, GN_EPS, st), 'hd_groupnorm_stats')
+            else:
+                s[1].run(st)
+        return self.out
+
+    @property
+    def num_launches(self):
+        return 4 * len(self.p.blocks)
+
+
+# ------------------------------------------------------------------------------------------------
+# IEF regressor -- src/models.py:80-116, 299-415
+# ------------------------------------------------------------------------------------------------
+class PackedIEFHead(object):
+    def __init__(self, w, scope, device, feat=2048, tc=False):
+        q = scope + '/3D_module'
+        W1 = np.asarray(w[q + '/fc1/weights'], np.float32)
+        self.d = W1.shape[0] - feat
+        self.feat = feat
+        # state = concat[phi, theta] (models.py:402): split fc1 so phi.W1[:feat] is computed once per window
+        self.fc1_phi = PackedConv(W1[:feat], device, post_shift=w[q + '/fc1/biases'], tc=tc)
+        self.fc1_theta = PackedConv(W1[feat:], device, post_relu=True)
+        self.fc2 = PackedConv(w[q + '/fc2/weights'], device, post_shift=w[q + '/fc2/biases'], post_relu=True, tc=tc)
+        self.fc3 = PackedConv(w[q + '/fc3/weights'], device, post_shift=w[q + '/fc3/biases'])
+
+
+class PackedIEF(object):
+    def __init__(self, w, device, scope='single_view_ief', delta_t_values=(-5, 5), tc=False):
+        self.device = device
+        self.main = PackedIEFHead(w, scope, device, tc=tc)
+        self.deltas = {}
+        for dt in delta_t_values:
+            dt = int(dt)
+            if dt == 0:
+                continue
+            sc = scope + ('_future%d' % dt if dt > 0 else '_past%d' % abs(dt))
+            self.deltas[dt] = PackedIEFHead(w, sc, device, tc=tc)
+        self.mean_param = _dev(np.asarray(w['mean_param'], np.float32).reshape(1, 85), device)
+
+
+class IEFPlan(object):
+    """call_hmr_ief for N rows: main 85-d head + 72-d delta heads started from the main prediction
+    (use_delta_from_pred=True, use_optcam=True as wired by tester.py:196-207)."""
+
+    def __init__(self, packed: PackedIEF, N, num_stage=3, delta_keys=None, impl='auto'):
+        self.p, self.N, self.num_stage = packed, N, num_stage
+        dev = packed.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.P = torch.empty((N, 1024), **f32)
+        self.h1 = torch.empty((N, 1024), **f32)
+        self.h2 = torch.empty((N, 1024), **f32)
+        self.theta = torch.empty((N, 85), **f32)
+        self.delta_keys = sorted(packed.deltas.keys()) if delta_keys is None else [k for k in delta_keys if k != 0]
+        D = max(1, len(self.delta_keys))
+        self.delta_all = torch.empty((N, D, 85), **f32)          # [N, D, 85]: the stacking of tester.py:252-253
+        self.delta_out = {dt: self.delta_all[:, i, :] for i, dt in enumerate(self.delta_keys)}
+        self.impl = impl
+        self._bound_for = None
+
+    def _head_ops(self, head, phi, start_view, state_view, ld):
+        """ops for one hmr_ief: start_view = theta_prev of stage 0, state_view = in-place theta afterwards."""
+        N = self.N
+        ops = [head.fc1_phi.bind(phi, N, 1, 1, self.P, impl=self.impl)]
+        for s in range(self.num_stage):
+            prev = start_view if s == 0 else state_view
+            prev_ld = start_view.stride(0) if s == 0 else ld
+            ops.append(head.fc1_theta.bind(prev, N, 1, 1, self.h1, in_ld=prev_ld, res=self.P, res_geom=(1024, 1, 1, 1), impl='simt'))
+            ops.append(head.fc2.bind(self.h1, N, 1, 1, self.h2, impl=self.impl))
+            ops.append(head.fc3.bind(self.h2, N, 1, 1, state_view, out_ld=ld, res=prev, res_geom=(prev_ld, 1, 1, 1), impl='simt'))
+        return ops
+
+    def _bind(self, phi, theta0):
+        self.main_ops = self._head_ops(self.p.main, phi, theta0, self.theta, 85)
+        self.delta_ops = {}
+        for dt in self.delta_keys:
+            view = self.delta_out[dt][:, 3:75]
+            self.delta_ops[dt] = self._head_ops(self.p.deltas[dt], phi, view, view, view.stride(0))
+        self._bound_for = (phi.data_ptr(), theta0.data_ptr())
+
+    def run(self, phi, theta0, stream=None):
+        """phi (N,2048), theta0 (N,85) contiguous -> (theta (N,85), {dt: (N,85) view of delta_all[:, i]})."""
+        st = current_stream() if stream is None else stream
+        if self._bound_for != (phi.data_ptr(), theta0.data_ptr()):
+            self._bind(phi, theta0)
+        for op in self.main_ops:
+            op.run(st)
+        for dt in self.delta_keys:
+            check(lib.hd_ief_delta_init(fptr(self.theta), fptr(self.delta_out[dt]), self.delta_out[dt].stride(0), self.N, st),
+                  'hd_ief_delta_init')
+            for op in self.delta_ops[dt]:
+                op.run(st)
+        return self.theta, self.delta_out
+
+    @property
+    def num_launches(self):
+        per = 1 + 3 * self.num_stage
+        return per + len(self.delta_keys) * (per + 1)
+
+
+def run_ief_head(head: PackedIEFHead, phi, start, num_stage=3, impl='auto', stream=None, out=None):
+    """hmr_ief for one head from an arbitrary start: phi (N,feat), start (N,d) (unit inner stride) -> (N,d).
+
+    Generic (binds descriptors on the fly); the Tester path uses the cached IEFPlan instead.
+    """
+    st = current_stream() if stream is None else stream
+    N, d = phi.shape[0], head.d
+    if start.shape[0] != N or start.shape[1] != d or start.stride(1) != 1:
+        raise _lib.HDError('hmr_ief: omega_start must be (N,%d) with unit inner stride' % d)
+    f32 = dict(dtype=torch.float32, device=phi.device)
+    P, h1, h2 = torch.empty((N, 1024), **f32), torch.empty((N, 1024), **f32), torch.empty((N, 1024), **f32)
+    theta = torch.empty((N, d), **f32) if out is None else out
+    ld = theta.stride(0)
+    head.fc1_phi.bind(phi, N, 1, 1, P, impl=impl).run(st)
+    for s in range(num_stage):
+        prev = start if s == 0 else theta
+        pld = prev.stride(0)
+        head.fc1_theta.bind(prev, N, 1, 1, h1, in_ld=pld, res=P, res_geom=(1024, 1, 1, 1), impl='simt').run(st)
+        head.fc2.bind(h1, N, 1, 1, h2, impl=impl).run(st)
+        head.fc3.bind(h2, N, 1, 1, theta, out_ld=ld, res=prev, res_geom=(pld, 1, 1, 1), impl='simt').run(st)
+    return theta

@@ -1,0 +1,134 @@
+/*
+ * hd_b200.h -- C-ABI of the B200-native HMMR video->SMPL hot path (libhd_b200.so).
+ *
+ * The reference (akanazawa/human_dynamics) is pure Python/TF1 and has no FFI layer; its
+ * boundary for this path is the Python call surface of graph-building functions plus one
+ * sess.run.  Each entry point below replaces the arithmetic of the cited
+ * reference function; the Python shim under src/ (same module paths, names and argument
+ * meaning as the reference) binds these with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions: every pointer is a DEVICE pointer to fp32 (or int32 where typed) unless it
+ * says "host"; tensors are row-major, activations NHWC; `stream` is a cudaStream_t passed
+ * as void*; all calls are asynchronous on `stream`, never synchronise, never allocate,
+ * and return an hd_status (0 = ok).  No torch types cross this boundary.
+ */
+#ifndef HD_B200_H_
+#define HD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HD_OK = 0,
+  HD_ERR_INVALID = 1,      /* bad shape / null pointer / unsupported combination */
+  HD_ERR_WORKSPACE = 2,    /* workspace too small */
+  HD_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed (see hd_last_error) */
+  HD_ERR_UNSUPPORTED = 4   /* device is not sm_100 or requested impl not available */
+} hd_status;
+
+int hd_version(void);
+const char *hd_status_string(int status);
+/* Last CUDA error text recorded by this thread's most recent failing call ("" if none). */
+const char *hd_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (host counter). */
+long long hd_launch_count(void);
+void hd_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused implicit-GEMM convolution / fully-connected layer.
+ * Replaces every slim conv2d / fully_connected (+ the BatchNorm/GroupNorm/ReLU/bias/residual
+ * ops around it) on the path: src/models.py:65-74 (resnet_v2_50 convs), :102-113 (IEF FCs),
+ * :173-184,:209-221 (temporal convs), :283-294 (fc2_res).
+ *
+ *   a[n,iy,ix,ci] = in[n,iy,ix,ci]                                (zero outside the image)
+ *   if pre_scale:  a = a*pre_scale[n*pre_img_stride+ci] + pre_shift[...]; if pre_relu: a=max(a,0)
+ *        (prologue acts on real pixels only: padding stays 0, like padding relu(bn(x)) in TF)
+ *   acc[n,oy,ox,co] = sum_{ky,kx,ci} a[n, oy*stride-pad_t+ky, ox*stride-pad_l+kx, ci] * W[(ky,kx,ci),co]
+ *   v = acc*post_scale[co] + post_shift[co]   (NULL scale = 1, NULL shift = 0)
+ *   if res: v += res[(n*res_H + oy*res_stride)*res_W + ox*res_stride][co]
+ *   if post_relu: v = max(v,0)
+ *   out[(n*Ho+oy)*Wo+ox][co] = v
+ * ------------------------------------------------------------------------------------------ */
+enum { HD_IMPL_SIMT = 0, HD_IMPL_TC_3XTF32 = 1, HD_IMPL_TC_1XTF32 = 2 };
+
+typedef struct {
+  const float *in;  long long in_ld;          /* floats between consecutive pixels (>= Cin) */
+  int n_img, H, W, Cin;
+  int Ho, Wo, KH, KW, stride, pad_t, pad_l;
+  const float *w_kn;                          /* [K, Cout] row-major, K=(ky,kx,ci) (TF HWIO flattened) */
+  const float *w_nk_hi;                       /* [Cout_pad, K_pad] K-major, tf32-truncated (tensor-core path) */
+  const float *w_nk_lo;                       /* residual w - w_hi, same layout (3xTF32 only) */
+  int Cout;  int K_pad;
+  const float *pre_scale, *pre_shift;  int pre_img_stride;  int pre_relu;
+  const float *post_scale, *post_shift;  int post_relu;
+  const float *res;  long long res_ld;  int res_H, res_W, res_stride;
+  float *out;  long long out_ld;
+  int impl;
+  const void *tmap_hi, *tmap_lo;              /* HOST pointers to 128-byte CUtensorMap blobs from hd_make_weight_tmap */
+} hd_conv_desc;
+
+int hd_conv_gemm(const hd_conv_desc *d, void *stream);
+
+/* Encode the TMA descriptor (CUtensorMap, 128 B, written to host memory `tmap_out`) for a K-major
+ * weight matrix [rows, k_pad] fp32 with a {32 x box_rows} box and 128-byte swizzle. */
+int hd_make_weight_tmap(const float *w_nk, int rows, int k_pad, int box_rows, void *tmap_out);
+
+/* ---- ResNet root / tail pieces (slim resnet_v2_50, called from src/models.py:65-74) ---- */
+/* conv1: 7x7 stride 2, explicit zero pad 3+3, + bias.  in [N,H,W,3] -> out [N,H/2,W/2,64]; w [7*7*3,64]. */
+int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *out, int N, int H, int W, void *stream);
+/* pool1: 3x3 stride 2 max pool, TF SAME padding (pad 0 top/left, 1 bottom/right for even sizes). */
+int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, void *stream);
+/* postnorm BN+ReLU then global mean over HxW: in [N,HW,C] -> out [N,C]. */
+int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, float *out, int N, int HW, int C, void *stream);
+
+/* ---- f_movie GroupNorm statistics (tf.contrib.layers.group_norm at src/models.py:155,188) ----
+ * x [B,T,C]; per (clip, group) mean / biased variance over T*(C/groups) elements (two-pass);
+ * gain[b,c] = rsqrt(var+eps)*gamma[c]; offset[b,c] = beta[c] - mean*gain[b,c]. */
+int hd_groupnorm_stats(const float *x, const float *gamma, const float *beta, float *gain, float *offset,
+                       int B, int T, int C, int groups, float eps, void *stream);
+
+/* ---- IEF glue (src/models.py:349-371): dst[n*dst_ld + :85] = [1, 0, 0, theta[n,3:75], theta[n,75:85]] ---- */
+int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *stream);
+
+/* ---- SMPL (src/tf_smpl/batch_smpl.py:26-162, batch_lbs.py:15-60,133-194, projection.py:16-29) ---- */
+typedef struct {
+  int num_verts, num_kps, lbs_nnz, kp_nnz_total;
+  const float *v_template;     /* [V*3] */
+  const float *dirs;           /* [10+207, V*3]: shapedirs rows then posedirs rows (batch_smpl.py:45-48,60-63) */
+  const float *J_template;     /* [24*3]  = J_regressor^T v_template */
+  const float *J_shapedirs;    /* [10, 24*3] = J_regressor^T shapedirs  (exact refactoring of batch_smpl.py:110-118) */
+  const int *lbs_idx;          /* [V, lbs_nnz] joint ids of the non-zero skinning weights (padded with weight 0) */
+  const float *lbs_w;          /* [V, lbs_nnz] */
+  const int *kp_ptr;           /* [K+1] CSC offsets into kp_vidx / kp_w (cocoplus_regressor, batch_smpl.py:76-82) */
+  const int *kp_vidx;          /* [kp_nnz_total] */
+  const float *kp_w;           /* [kp_nnz_total] */
+  int parents[24];             /* kintree_table[0] as int32 (root -1), batch_smpl.py:66 */
+} hd_smpl_consts;
+
+size_t hd_smpl_workspace_bytes(int N);
+/* beta rows of 10 at stride beta_ld, theta rows of 72 at stride theta_ld, cam rows of 3 at stride cam_ld (so the
+ * three can alias columns [75:85], [3:75], [0:3] of one [N,85] omega buffer, src/omega.py:231-235).
+ * verts [N,V,3], joints [N,K,3], Rs [N,24,3,3], Jtr [N,24,3]; cam + kps [N,K,2] optional (both or neither).
+ * Any output pointer except verts may be NULL.  Pose n lands in output slot n*out_mul + out_off of every output
+ * array (out_mul=1, out_off=0 = dense), so D delta heads can write the [B,T,D,...] stacking of tester.py:252-253
+ * in place. */
+int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N,
+                    float *verts, float *joints, float *Rs, float *Jtr,
+                    const float *cam, int cam_ld, float *kps, int out_mul, int out_off,
+                    void *ws, size_t ws_bytes, void *stream);
+/* batch_rodrigues: theta [M,3] -> R [M,3,3]. */
+int hd_rodrigues(const float *theta, float *R, int M, void *stream);
+/* batch_global_rigid_transformation: Rs [N,24,3,3], Js [N,24,3], parents host int[24] -> new_J [N,24,3], A [N,24,4,4]. */
+int hd_global_rigid(const float *Rs, const float *Js, const int *parents_host, float *new_J, float *A44, int N,
+                    int rotate_base, void *stream);
+/* batch_orth_proj_idrot: X [N,P,3], cam [N,3] -> out [N,P,2]. */
+int hd_orth_proj(const float *X, const float *cam, float *out, int N, int P, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HD_B200_H_ */

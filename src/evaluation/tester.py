@@ -1,0 +1,101 @@
+"""Tester -- drop-in for the reference's src/evaluation/tester.py (inference graph + predict).
+
+`Tester(config).predict(images)` returns the same 14-key dict of numpy arrays as the reference's
+`sess.run(fetch_dict)` (tester.py:217-258); `predict_all_images` is the sliding-window driver
+(tester.py:260-312).  The graph is replaced by an HMMREngine plan on the current CUDA device.
+"""
+import os
+
+import numpy as np
+import torch
+
+from human_dynamics_b200 import runtime as _rt
+from human_dynamics_b200.engine import HMMREngine, load_weights
+
+
+class Tester(object):
+
+    def __init__(self, config, pretrained_resnet_path='', sequence_length=None, engine=None):
+        self.config = config
+        self.load_path = getattr(config, 'load_path', '')
+        weights = getattr(config, 'weights', None)
+        if engine is None and weights is None:
+            if not self.load_path:
+                raise Exception('[!] You need to specify `load_path` to load a pretrained model')     # tester.py:31-34
+            if not os.path.exists(self.load_path):
+                raise Exception('{} doesnt exist..'.format(self.load_path))                           # tester.py:35-38 (no ipdb)
+            weights = load_weights(self.load_path)
+        if pretrained_resnet_path:                                                                    # tester.py:99-109
+            rw = load_weights(pretrained_resnet_path)
+            weights = dict(weights)
+            weights.update({k: v for k, v in rw.items() if k.startswith('resnet_v2_50')})
+
+        self.batch_size = config.batch_size
+        self.sequence_length = sequence_length if sequence_length else config.sequence_length
+        self.pred_mode = config.pred_mode
+        self.num_conv_layers = config.num_conv_layers
+        self.fov = self.num_conv_layers * 4 + 1                                                       # tester.py:48
+        self.delta_t_values = [int(dt) for dt in config.delta_t_values]
+        self.img_size = getattr(config, 'img_size', 224)
+        self.num_output = 85
+        smpl_model = getattr(config, 'smpl_model', None) or getattr(config, 'smpl_model_path', '')
+        self.engine = engine if engine is not None else HMMREngine(weights, smpl_model, config)
+        self.smpl = self.engine.smpl
+        _rt.set_default_engine(self.engine)
+        self._pinned = {}
+
+    def predict(self, images, as_numpy=True):
+        """Runs forward pass of model.  images (BxTxHxWx3) numpy / torch (host or device) -> dict."""
+        B, T = self.batch_size, self.sequence_length
+        exp = (B, T, self.img_size, self.img_size, 3)
+        if tuple(images.shape) != exp:
+            raise ValueError('images must have the static shape %s baked at construction (tester.py:64-66), got %s'
+                             % (exp, tuple(images.shape)))
+        dev = self.engine.device
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+        if not images.is_cuda:
+            images = images.to(dev, dtype=torch.float32, non_blocking=True)
+        out = self.engine.predict(images.float())
+        out = {k: v for k, v in out.items() if not k.startswith('_')}
+        if not as_numpy:
+            return out
+        return self._fetch(out)
+
+    def _fetch(self, out):
+        """Device -> pinned host -> numpy: the result half of the one host<->device crossing (tester.py:257)."""
+        res = {}
+        for k, v in out.items():
+            key = (k, tuple(v.shape))
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
+            self._pinned[key].copy_(v, non_blocking=True)
+            res[k] = self._pinned[key]
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy().copy() for k, v in res.items()}
+
+    def predict_all_images(self, all_images):
+        """Sliding-window prediction over a whole sequence (tester.py:260-312).  all_images: N x H x W x 3."""
+        B, T = self.batch_size, self.sequence_length
+        N = len(all_images)
+        H, W = self.img_size, self.img_size
+        margin = (self.fov - 1) // 2
+        g = self.sequence_length - 2 * margin
+        if g <= 0:
+            raise ValueError('sequence_length %d leaves no frame with full field of view %d' % (T, self.fov))
+        count = int(np.ceil(N / (g * B)))
+        num_fill = count * B * g + T - N
+        all_images = np.asarray(all_images, dtype=np.float32)
+        images_padded = np.concatenate((np.zeros((margin, H, W, 3), np.float32), all_images,
+                                        np.zeros((num_fill, H, W, 3), np.float32)), axis=0)
+        results = {}
+        for c in range(count):
+            batch = np.stack([images_padded[(c * B + i) * g:(c * B + i) * g + T] for i in range(B)])
+            pred = self.predict(batch)
+            for k, v in pred.items():
+                results.setdefault(k, []).append(v)
+        new_results = {}
+        for k, v in results.items():
+            v = np.array(v)[:, :, margin:-margin]
+            new_results[k] = v.reshape((-1,) + v.shape[3:])[:N]
+        return new_results

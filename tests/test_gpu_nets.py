@@ -1,0 +1,264 @@
+"""GPU parity: fused conv/FC kernel, ResNet-v2-50, f_movie, IEF and the full Tester window vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+def rel_err(a, b):
+    b = np.asarray(b, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def _conv_case(rng, n, H, W, Cin, Cout, KH, KW, stride, pad, pre=None, res=None, post_scale=True, relu=True, impl='simt'):
+    """Run hd_conv_gemm through PackedConv and compare with an fp64 torch reference."""
+    from human_dynamics_b200.nets import PackedConv
+    x = rng.normal(0, 1, size=(n, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(0, 1, size=(KH, KW, Cin, Cout)) / np.sqrt(KH * KW * Cin)).astype(np.float32)
+    ps = rng.uniform(0.5, 1.5, size=Cout).astype(np.float32) if post_scale else None
+    pb = rng.normal(0, 0.2, size=Cout).astype(np.float32)
+    dev = torch.device('cuda')
+    pc = PackedConv(w, dev, ps, pb, relu, stride=stride, pad=pad, tc=(impl != 'simt'))
+    xt = torch.from_numpy(x).to(dev)
+    pre_t = None
+    a = torch.from_numpy(x).double()
+    if pre == 'bn':
+        s = rng.uniform(0.5, 1.5, size=Cin).astype(np.float32); b = rng.normal(0, 0.3, size=Cin).astype(np.float32)
+        pre_t = (torch.from_numpy(s).to(dev), torch.from_numpy(b).to(dev), 0, 1)
+        a = torch.relu(a * torch.from_numpy(s).double() + torch.from_numpy(b).double())
+    elif pre == 'gn':
+        s = rng.uniform(0.5, 1.5, size=(n, Cin)).astype(np.float32); b = rng.normal(0, 0.3, size=(n, Cin)).astype(np.float32)
+        pre_t = (torch.from_numpy(s).to(dev), torch.from_numpy(b).to(dev), Cin, 1)
+        a = torch.relu(a * torch.from_numpy(s).double()[:, None, None, :] + torch.from_numpy(b).double()[:, None, None, :])
+    ac = F.pad(a.permute(0, 3, 1, 2), (pad[1], pad[1], pad[0], pad[0]))
+    y = F.conv2d(ac, torch.from_numpy(w).double().permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+    Ho, Wo = y.shape[1], y.shape[2]
+    if ps is not None:
+        y = y * torch.from_numpy(ps).double()
+    y = y + torch.from_numpy(pb).double()
+    res_t, res_geom = None, None
+    if res is not None:
+        rs = res
+        r = rng.normal(0, 1, size=(n, Ho * rs, Wo * rs, Cout)).astype(np.float32)
+        res_t = torch.from_numpy(r).to(dev)
+        res_geom = (Cout, Ho * rs, Wo * rs, rs)
+        y = y + torch.from_numpy(r).double()[:, ::rs, ::rs, :]
+    if relu:
+        y = torch.relu(y)
+    out = torch.empty((n, Ho, Wo, Cout), dtype=torch.float32, device=dev)
+    op = pc.bind(xt, n, H, W, out, pre=pre_t, res=res_t, res_geom=res_geom, impl=impl)
+    assert op.out_hw == (Ho, Wo)
+    op.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return rel_err(out.cpu().numpy(), y.numpy()), op
+
+
+CASES = [
+    # n, H, W, Cin, Cout, KH, KW, stride, pad, pre, res, post_scale, relu
+    (2, 14, 14, 64, 64, 1, 1, 1, (0, 0), 'bn', None, True, True),
+    (2, 14, 14, 64, 256, 1, 1, 1, (0, 0), None, 1, False, False),
+    (3, 9, 9, 32, 96, 3, 3, 1, (1, 1), None, None, True, True),
+    (2, 14, 14, 64, 64, 3, 3, 2, (1, 1), None, None, True, True),
+    (2, 8, 8, 128, 512, 1, 1, 1, (0, 0), None, 2, False, False),       # strided identity shortcut
+    (3, 20, 1, 128, 128, 3, 1, 1, (1, 0), 'gn', 1, False, False),       # temporal conv + GN prologue + residual
+    (37, 1, 1, 85, 1024, 1, 1, 1, (0, 0), None, 1, False, True),        # ragged K (IEF fc1 theta part)
+    (37, 1, 1, 1024, 85, 1, 1, 1, (0, 0), None, 1, False, False),       # ragged N (IEF fc3)
+    (2, 12, 12, 3, 64, 7, 7, 2, (3, 3), None, None, False, False),      # conv1 geometry
+    (1, 5, 5, 40, 24, 3, 3, 1, (1, 1), 'bn', None, True, True),         # nothing aligned
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_gemm_simt(case):
+    rng = np.random.RandomState(hash(case) % (2 ** 31))
+    err, _ = _conv_case(rng, *case, impl='simt')
+    assert err < 2e-5, err
+
+
+TC_CASES = [c for c in CASES if c[3] % 32 == 0] + [
+    (4, 28, 28, 128, 128, 3, 3, 1, (1, 1), None, None, True, True),
+    (4, 28, 28, 256, 64, 1, 1, 1, (0, 0), 'bn', None, True, True),
+    (2, 7, 7, 512, 2048, 1, 1, 1, (0, 0), None, 1, False, False),
+    (5, 20, 1, 2048, 2048, 3, 1, 1, (1, 0), 'gn', 1, False, False),
+    (640, 1, 1, 2048, 1024, 1, 1, 1, (0, 0), None, None, False, False),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_gemm_tcgen05_3xtf32(case):
+    from human_dynamics_b200 import _lib
+    rng = np.random.RandomState(hash(case) % (2 ** 31))
+    err, op = _conv_case(rng, *case, impl='tc3')
+    assert op.d.impl == _lib.HD_IMPL_TC_3XTF32, 'tensor-core path was not selected'
+    assert err < 2e-5, err
+
+
+def test_conv_gemm_tcgen05_1xtf32_is_tf32_accurate():
+    rng = np.random.RandomState(3)
+    err, _ = _conv_case(rng, 4, 28, 28, 128, 128, 3, 3, 1, (1, 1), None, None, True, True, impl='tc1')
+    assert 1e-5 < err < 5e-3, err          # single-pass TF32: ~1e-3, NOT the parity mode
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('n,size', [(3, 64), (2, 224)])
+def test_resnet_matches_oracle(weights, impl, n, size):
+    from human_dynamics_b200 import synthetic
+    from human_dynamics_b200.nets import PackedResNet, ResNetPlan
+    from oracle import nets_ref
+    img = synthetic.make_images(n, seed=n, size=size)
+    dev = torch.device('cuda')
+    plan = ResNetPlan(PackedResNet(weights, dev, tc=(impl != 'simt')), n, size, impl)
+    phi = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    plan.run(torch.from_numpy(img).to(dev), phi)
+    torch.cuda.synchronize()
+    ref = nets_ref.encoder_resnet(img, weights).numpy()
+    ref64 = nets_ref.encoder_resnet(img, weights, torch.float64).numpy()
+    assert rel_err(ref, ref64) < 1e-5
+    assert rel_err(phi.cpu().numpy(), ref) < REL
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_fmovie_matches_oracle(weights, impl):
+    from human_dynamics_b200.nets import PackedFMovie, FMoviePlan
+    from oracle import nets_ref
+    B, T = 3, 20
+    x = np.random.RandomState(0).normal(0, 1, size=(B, T, 2048)).astype(np.float32)
+    dev = torch.device('cuda')
+    plan = FMoviePlan(PackedFMovie(weights, dev, 3, tc=(impl != 'simt')), B, T, impl)
+    y = plan.run(torch.from_numpy(x).to(dev))
+    torch.cuda.synchronize()
+    ref = nets_ref.az_fc2_groupnorm(x, weights, 3).numpy()
+    assert rel_err(y.cpu().numpy(), ref) < REL
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_ief_matches_oracle(weights, impl):
+    from human_dynamics_b200.nets import PackedIEF, IEFPlan
+    from oracle import nets_ref
+    N = 45
+    phi = np.random.RandomState(1).normal(0, 1, size=(N, 2048)).astype(np.float32)
+    dev = torch.device('cuda')
+    packed = PackedIEF(weights, dev, tc=(impl != 'simt'))
+    plan = IEFPlan(packed, N, impl=impl)
+    theta0 = packed.mean_param.expand(N, 85).contiguous()
+    theta, deltas = plan.run(torch.from_numpy(phi).to(dev), theta0)
+    torch.cuda.synchronize()
+    om = np.tile(weights['mean_param'].reshape(1, 85), (N, 1))
+    rt, rd = nets_ref.call_hmr_ief(phi, om, weights, 'single_view_ief', 85, 3, (0, -5, 5), True, True)
+    assert rel_err(theta.cpu().numpy(), rt.numpy()) < REL
+    for dt in (-5, 5):
+        assert rel_err(deltas[dt].cpu().numpy(), rd[dt].numpy()) < REL
+
+
+def _check_predict(got, ref, keys=None):
+    for k, v in ref.items():
+        if k.startswith('_') or (keys and k not in keys):
+            continue
+        g = got[k].cpu().numpy() if isinstance(got[k], torch.Tensor) else got[k]
+        assert g.shape == v.shape, (k, g.shape, v.shape)
+        assert rel_err(g, v) < REL, (k, rel_err(g, v))
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_full_window_matches_oracle(weights, smpl_model, impl):
+    """BASELINE config 3 wiring at B=2, T=20, 224x224 (oracle ResNet on 40 frames takes ~10 s)."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from human_dynamics_b200.engine import HMMREngine
+    from oracle import nets_ref
+    B, T = 2, 20
+    img = synthetic.make_images(B * T, seed=0).reshape(B, T, 224, 224, 3)
+    eng = HMMREngine(weights, smpl_model, HMMRConfig(batch_size=B, sequence_length=T, frame_chunk=16), impl=impl)
+    got = eng.predict(torch.from_numpy(img).cuda())
+    torch.cuda.synchronize()
+    ref = nets_ref.hmmr_predict(img, weights, smpl_model)
+    assert rel_err(got['_phi'].cpu().numpy(), ref['_phi']) < REL
+    assert rel_err(got['_movie_strips'].cpu().numpy(), ref['_movie_strips']) < REL
+    _check_predict(got, ref)
+
+
+def test_single_frame_path_matches_oracle(weights, smpl_model):
+    """BASELINE config 2 wiring (ResNet + 3-iter IEF + SMPL, no temporal encoder) at batch 8."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from human_dynamics_b200.engine import HMMREngine
+    from oracle import nets_ref
+    n = 8
+    img = synthetic.make_images(n, seed=4)
+    eng = HMMREngine(weights, smpl_model, HMMRConfig(batch_size=n, sequence_length=1))
+    got = eng.predict(torch.from_numpy(img).cuda().view(n, 1, 224, 224, 3), single_frame=True)
+    torch.cuda.synchronize()
+    ref = nets_ref.single_frame_predict(img, weights, smpl_model)
+    for k in ('omegas', 'verts', 'joints', 'kps', 'poses'):
+        assert rel_err(got[k].cpu().numpy().reshape(ref[k].shape), ref[k]) < REL, k
+
+
+def test_tester_surface_and_sliding_window(weights, smpl_model):
+    """src.evaluation.tester.Tester: predict() dict contract and predict_all_images windowing (tester.py:260-312)."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from src.evaluation.tester import Tester
+    from oracle import nets_ref
+    B, T, S = 2, 20, 64
+    cfg = HMMRConfig(batch_size=B, sequence_length=T, img_size=S, weights=weights, smpl_model=smpl_model, pred_mode='pred')
+    tester = Tester(cfg)
+    N = 19                                        # -> count = ceil(19 / (8*2)) = 2 passes, ragged tail
+    frames = synthetic.make_images(N, seed=9, size=S)
+    res = tester.predict_all_images(frames)
+    margin, g = 6, 8
+    count = int(np.ceil(N / (g * B)))
+    padded = np.concatenate([np.zeros((margin, S, S, 3), np.float32), frames,
+                             np.zeros((count * B * g + T - N, S, S, 3), np.float32)])
+    ref_chunks = []
+    for c in range(count):
+        batch = np.stack([padded[(c * B + i) * g:(c * B + i) * g + T] for i in range(B)])
+        ref_chunks.append(nets_ref.hmmr_predict(batch, weights, smpl_model))
+    for k in ('verts', 'omegas', 'kps', 'joints', 'poses', 'cams', 'shapes', 'verts_delta', 'omegas_delta', 'kps_delta'):
+        v = np.array([r[k] for r in ref_chunks])[:, :, margin:-margin]
+        v = v.reshape((-1,) + v.shape[3:])[:N]
+        assert res[k].shape == v.shape, k
+        assert rel_err(res[k], v) < REL, k
+    assert set(res.keys()) == {a + b for a in ('cams', 'joints', 'kps', 'poses', 'shapes', 'verts', 'omegas') for b in ('', '_delta')}
+    with pytest.raises(ValueError):
+        tester.predict(np.zeros((1, T, S, S, 3), np.float32))     # static shapes, like the TF placeholder
+
+
+def test_hal_mode_and_models_surface(weights, smpl_model):
+    """pred_mode='hal' (fc2_res) and the reference-named functions in src.models / src.omega."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from src.evaluation.tester import Tester
+    import src.models as M
+    from src.omega import OmegasPred, f_movie
+    from oracle import nets_ref
+    B, T, S = 2, 5, 64
+    cfg = HMMRConfig(batch_size=B, sequence_length=T, img_size=S, weights=weights, smpl_model=smpl_model, pred_mode='hal')
+    tester = Tester(cfg)
+    img = synthetic.make_images(B * T, seed=2, size=S).reshape(B, T, S, S, 3)
+    got = tester.predict(img)
+    ref = nets_ref.hmmr_predict(img, weights, smpl_model, pred_mode='hal')
+    _check_predict(got, ref)
+    # stateless functions resolve weights through the active engine
+    x = torch.from_numpy(img.reshape(B * T, S, S, 3)).cuda()
+    phi, scope = M.get_image_encoder()(x, is_training=False, reuse=False)
+    assert scope == 'resnet_v2_50'
+    assert rel_err(phi.cpu().numpy(), ref['_phi'].reshape(B * T, -1)) < REL
+    strips = M.get_temporal_encoder()(is_training=False, net=phi.view(B, T, -1), num_conv_layers=3)
+    assert f_movie is M.az_fc2_groupnorm
+    assert rel_err(strips.cpu().numpy(), nets_ref.az_fc2_groupnorm(ref['_phi'], weights, 3).numpy()) < REL
+    om = torch.from_numpy(np.tile(weights['mean_param'].reshape(1, 85), (B * T, 1))).cuda()
+    theta, deltas = M.call_hmr_ief(phi, om, 'single_view_ief', 85, 3, False, (0, -5, 5), True, True)
+    rt, rd = nets_ref.call_hmr_ief(ref['_phi'].reshape(B * T, -1), om.cpu().numpy(), weights, 'single_view_ief', 85, 3,
+                                   (0, -5, 5), True, True)
+    assert rel_err(theta.cpu().numpy(), rt.numpy()) < REL
+    assert rel_err(deltas[5].cpu().numpy(), rd[5].numpy()) < REL
+    # OmegasPred container: append_batched -> compute_smpl -> getters (omega.py:237-304)
+    from src.tf_smpl.batch_smpl import SMPL
+    op = OmegasPred(cfg, SMPL(smpl_model), use_optcam=False, vis_max_batch=B, batch_size=B, is_training=False)
+    op.append_batched(theta.view(B, T, 85))
+    OmegasPred.compute_all_smpl([op])
+    from oracle.smpl_ref import SMPLRef
+    raw = rt.numpy()
+    v_ref, _, _ = SMPLRef(smpl_model)(raw[:, 75:], raw[:, 3:75], get_skin=True)
+    assert rel_err(op.get_verts().cpu().numpy().reshape(v_ref.shape), v_ref) < REL
+    assert op.get_kps().shape == (B, T, 25, 2) and op.get_poses_rot().shape == (B, T, 24, 3, 3)
