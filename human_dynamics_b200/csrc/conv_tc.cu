@@ -1,9 +1,401 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 implicit-GEMM convolution / FC for sm_100a with FP32-class accuracy via 3xTF32 error compensation.
+//
+//   D[128 x BN] (fp32, TMEM)  +=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        per 32-wide K chunk
+//
+// A (activations) never exists in HBM in im2col form: four producer warps gather the 128 x 32 fp32 tile
+// (zero padding, stride, per-channel BN/GN affine + ReLU prologue fused), split every value into its
+// TF32-exact head `hi` (low 13 mantissa bits cleared -- exactly what the tensor core would read) and the
+// fp32 remainder `lo = x - hi`, and store both straight into the 128-byte-swizzled K-major layout that the
+// UMMA shared-memory descriptor expects.  B (weights, pre-split offline into hi/lo, K-major) arrives by TMA.
+// One elected thread issues tcgen05.mma.kind::tf32; accumulators live in TMEM and are read back with
+// tcgen05.ld for the fused epilogue (per-channel scale/shift, residual add, ReLU).
+//
+// Warp roles (192 threads):  0-3 A producers, then epilogue (TMEM lane quarter = warp id);
+//                            4   TMEM allocator + TMA producer for B;   5   MMA issuer.
+#include <cuda.h>
 #include "conv_common.cuh"
+
 namespace hd {
-int launch_conv_tc(const ConvParams &, const hd_conv_desc *, cudaStream_t) {
-  set_last_error_text("tcgen05 path not built");
-  return HD_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-extern "C" int hd_make_weight_tmap(const float *, int, int, int, void *) { return HD_ERR_UNSUPPORTED; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // LBO (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                // SBO [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version [46,48)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B [61,64)
+  return d;
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;   // + barriers + alignment slack
+  // kind::tf32, D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2, N>>3 [17,23), M>>4 [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + C::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_k = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 5);     // 4 producer warps + 1 arrive.expect_tx from the TMA lane
+      mbar_init(empty_bar(s), 1);    // tcgen05.commit
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // =============================== A producers ===============================
+    const int t = threadIdx.x;            // 0..127
+    const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
+    const int rb = t >> 3;                // rows rb + 16*i
+    const uint32_t sw_off = (uint32_t)((j ^ (rb & 7)) << 4);
+    int rn[8], riy[8], rix[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rb + 16 * i;
+      if (m < p.M) {
+        const int hw = p.Ho * p.Wo;
+        const int n = m / hw;
+        const int r = m - n * hw;
+        const int oy = r / p.Wo, ox = r - oy * p.Wo;
+        rn[i] = n; riy[i] = oy * p.stride - p.pad_t; rix[i] = ox * p.stride - p.pad_l;
+      } else {
+        rn[i] = -1; riy[i] = 0; rix[i] = 0;
+      }
+    }
+    float4 cur[8], nxt[8];
+    uint32_t vmask_cur = 0, vmask_nxt = 0;
+    auto gather = [&](int kc, float4 *dst, uint32_t &vmask) {
+      const int kb = kc * BK;
+      const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * 4;
+      const int ky = tap / p.KW, kx = tap - ky * p.KW;
+      vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = riy[i] + ky, ix = rix[i] + kx;
+        const bool ok = rn[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        if (ok) {
+          dst[i] = __ldg(reinterpret_cast<const float4 *>(p.in + ((size_t)((size_t)rn[i] * p.H + iy) * p.W + ix) * p.in_ld + ci));
+          vmask |= 1u << i;
+        } else {
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    if (num_k > 0) gather(0, cur, vmask_cur);
+    for (int kc = 0; kc < num_k; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+      if (kc + 1 < num_k) gather(kc + 1, nxt, vmask_nxt);       // keep the next chunk's loads in flight
+      // prologue: per-channel affine (+ReLU) on real pixels only
+      if (p.pre_scale) {
+        const int kb = kc * BK;
+        const int ci = kb % p.Cin + j * 4;
+        float4 sc, sh;
+        if (p.pre_img_stride == 0) {
+          sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + ci));
+          sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + ci));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!(vmask_cur & (1u << i))) continue;
+          if (p.pre_img_stride != 0) {
+            sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + (size_t)rn[i] * p.pre_img_stride + ci));
+            sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + (size_t)rn[i] * p.pre_img_stride + ci));
+          }
+          float4 v = cur[i];
+          v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+          if (p.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          cur[i] = v;
+        }
+      }
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      uint8_t *a_hi = smem + s * C::STAGE_BYTES;
+      uint8_t *a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = (uint32_t)(rb + 16 * i) * 128u + sw_off;
+        const float4 v = cur[i];
+        float4 hi;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4 *>(a_hi + off) = hi;
+        if (SPLIT) *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      vmask_cur = vmask_nxt;
+    }
+
+    // =============================== epilogue ===============================
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + warp * 32 + lane;
+    const bool mvalid = m < p.M;
+    size_t res_row = 0;
+    if (p.res && mvalid) {
+      const int hw = p.Ho * p.Wo;
+      const int n = m / hw;
+      const int r = m - n * hw;
+      const int oy = r / p.Wo, ox = r - oy * p.Wo;
+      res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);   // whole warp: .sync.aligned
+      if (!mvalid) continue;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int co = n0 + c0 + q * 4;
+        if (co >= p.Cout) break;
+        float x[4] = {__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                      __uint_as_float(v[q * 4 + 3])};
+        if (p.vec_out) {
+          if (p.post_scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.post_scale + co));
+            x[0] *= sc.x; x[1] *= sc.y; x[2] *= sc.z; x[3] *= sc.w;
+          }
+          if (p.post_shift) {
+            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.post_shift + co));
+            x[0] += sh.x; x[1] += sh.y; x[2] += sh.z; x[3] += sh.w;
+          }
+          if (p.res) {
+            const float4 r = *reinterpret_cast<const float4 *>(p.res + res_row * p.res_ld + co);
+            x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+          }
+          if (p.post_relu) { x[0] = fmaxf(x[0], 0.f); x[1] = fmaxf(x[1], 0.f); x[2] = fmaxf(x[2], 0.f); x[3] = fmaxf(x[3], 0.f); }
+          *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (co + e >= p.Cout) continue;
+            float y = x[e];
+            if (p.post_scale) y *= __ldg(p.post_scale + co + e);
+            if (p.post_shift) y += __ldg(p.post_shift + co + e);
+            if (p.res) y += p.res[res_row * p.res_ld + co + e];
+            if (p.post_relu) y = fmaxf(y, 0.f);
+            p.out[(size_t)m * p.out_ld + co + e] = y;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 4) {
+    // =============================== B producer (TMA) ===============================
+    if (lane == 0) {
+      for (int kc = 0; kc < num_k; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t b_hi = smem_base + s * C::STAGE_BYTES + 2 * A_TILE_BYTES;
+        mbar_arrive_expect_tx(full_bar(s), SPLIT ? 2 * C::B_TILE_BYTES : C::B_TILE_BYTES);
+        tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BK, n0);
+        if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BK, n0);
+      }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      for (int kc = 0; kc < num_k; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+        const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+        const uint64_t da_hi = make_smem_desc(a_hi), da_lo = make_smem_desc(a_lo);
+        const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_lo);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {           // UMMA K = 8 for tf32 -> advance 32 bytes inside the swizzle atom
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          if (SPLIT) {
+            umma_tf32(tmem_d, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);   // small terms first
+            umma_tf32(tmem_d, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, C::IDESC, 1u);
+          } else {
+            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+          }
+        }
+        umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);                    // accumulator complete -> epilogue
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+template <int BN, bool SPLIT>
+int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
+    configured = true;
+  }
+  alignas(64) CUtensorMap thi, tlo;
+  memcpy(&thi, d->tmap_hi, sizeof(CUtensorMap));
+  memcpy(&tlo, d->tmap_lo ? d->tmap_lo : d->tmap_hi, sizeof(CUtensorMap));
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, BN));
+  conv_gemm_tc_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  return check_launch("conv_gemm_tc_kernel");
+}
+
+}  // namespace
+
+int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
+  if (!d->tmap_hi || (d->impl == HD_IMPL_TC_3XTF32 && !d->tmap_lo)) {
+    set_last_error_text("hd_conv_gemm(tc): missing tensor maps");
+    return HD_ERR_INVALID;
+  }
+  if (p.Cin % BK != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % BK != 0 ||
+      (p.pre_scale && (!aligned16(p.pre_scale) || !aligned16(p.pre_shift) || p.pre_img_stride % 4 != 0))) {
+    set_last_error_text("hd_conv_gemm(tc): needs Cin % 32 == 0 and 16-byte aligned input / prologue vectors");
+    return HD_ERR_INVALID;
+  }
+  const bool split = d->impl == HD_IMPL_TC_3XTF32;
+  if (p.Cout <= 64) return split ? launch_tc<64, true>(p, d, st) : launch_tc<64, false>(p, d, st);
+  return split ? launch_tc<128, true>(p, d, st) : launch_tc<128, false>(p, d, st);
+}
+
+}  // namespace hd
+
+// K-major weight matrix [rows, k_pad] fp32 -> CUtensorMap with a {32 x box_rows} box, 128-byte swizzle.
+// box_rows must equal the kernel's N tile: 64 when Cout <= 64, else 128.
+extern "C" int hd_make_weight_tmap(const float *w_nk, int rows, int k_pad, int box_rows, void *tmap_out) {
+  HD_REQUIRE(w_nk && tmap_out && rows > 0 && k_pad > 0 && k_pad % 32 == 0 && (box_rows == 64 || box_rows == 128) &&
+                 rows % box_rows == 0 && hd::aligned16(w_nk),
+             "hd_make_weight_tmap: bad arguments");
+  hd::EncodeTiledFn fn = hd::get_encode_fn();
+  if (!fn) { hd::set_last_error_text("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return HD_ERR_UNSUPPORTED; }
+  alignas(64) CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)k_pad * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w_nk), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    hd::set_last_error_text(msg);
+    return HD_ERR_CUDA;
+  }
+  memcpy(tmap_out, &tm, sizeof(tm));
+  return HD_OK;
+}

@@ -65,7 +65,8 @@ class PackedConv(object):
         self.K_pad = 0
         if tc and self.Cin % 32 == 0:
             self.K_pad = self.K
-            rows = (self.Cout + 127) // 128 * 128
+            box = 64 if self.Cout <= 64 else 128              # must equal the kernel's N tile (conv_tc.cu)
+            rows = (self.Cout + box - 1) // box * box
             w_nk = np.zeros((rows, self.K_pad), np.float32)
             w_nk[:self.Cout] = w_kn.T
             hi, lo = tf32_split(w_nk)
@@ -73,9 +74,9 @@ class PackedConv(object):
             self.w_nk_lo = _dev(lo, device)
             self.tmap_hi = (C.c_ubyte * 128)()
             self.tmap_lo = (C.c_ubyte * 128)()
-            check(lib.hd_make_weight_tmap(fptr(self.w_nk_hi), rows, self.K_pad, 128, C.cast(self.tmap_hi, C.c_void_p)),
+            check(lib.hd_make_weight_tmap(fptr(self.w_nk_hi), rows, self.K_pad, box, C.cast(self.tmap_hi, C.c_void_p)),
                   'hd_make_weight_tmap')
-            check(lib.hd_make_weight_tmap(fptr(self.w_nk_lo), rows, self.K_pad, 128, C.cast(self.tmap_lo, C.c_void_p)),
+            check(lib.hd_make_weight_tmap(fptr(self.w_nk_lo), rows, self.K_pad, box, C.cast(self.tmap_lo, C.c_void_p)),
                   'hd_make_weight_tmap')
             self.tc = True
 
