@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the HMMR video->SMPL hot path (BASELINE.json metric: frames/sec through
+ResNet-v2-50 -> f_movie -> IEF -> SMPL LBS -> projection).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference ...                     the reference path restated on the host CPU cores
+                                                           (TF 1.8 cannot be installed here: oracle port)
+
+Prints ONE JSON line (rank 0).  Workloads: hmmr (BASELINE config 3: 32 clips x T=20, the default; weak-scaled
+to 32 clips per GPU = config 4 at 8 GPUs), single_frame (config 2: batch 64), smpl (config 5: 65536 poses).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic work per unit (SURVEY.md 8d / DESIGN.md): dense FLOPs as the reference computes them
+FLOP_RESNET_FRAME = 6.960e9
+FLOP_FMOVIE_FRAME = 0.146e9
+FLOP_IEF_FRAME_3HEADS = 59.4e6
+FLOP_SMPL_POSE = 16.5e6
+BYTES_SMPL_POSE = 84384
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d['bf16_tflops_sustained'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, clips_per_step=1, T=20):
+    import torch
+    from human_dynamics_b200 import synthetic
+    from oracle import nets_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = synthetic.make_synthetic_weights(seed=1)
+    smpl = synthetic.make_synthetic_smpl(seed=2)
+    times = []
+    if workload == 'smpl':
+        from oracle.smpl_ref import SMPLRef, batch_orth_proj_idrot
+        n = 256
+        beta, theta = synthetic.make_smpl_inputs(n, seed=0)
+        cam = np.ones((n, 3), np.float32)
+        ref = SMPLRef(smpl)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            v, j, _ = ref(beta, theta, get_skin=True)
+            batch_orth_proj_idrot(j, cam)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        units, sample = n, '%d poses per step (numpy float32 port of batch_smpl.py)' % n
+    elif workload == 'single_frame':
+        n = 8
+        img = synthetic.make_images(n, seed=0)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            nets_ref.single_frame_predict(img, w, smpl)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        units, sample = n, '%d frames per step (torch-CPU float32 port, reference op order)' % n
+    else:
+        img = synthetic.make_images(clips_per_step * T, seed=0).reshape(clips_per_step, T, 224, 224, 3)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            nets_ref.hmmr_predict(img, w, smpl)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        units = clips_per_step * T
+        sample = '%d clip(s) x T=%d frames per step (torch-CPU float32 port of the TF1 graph, reference op order)' % (clips_per_step, T)
+    sec = float(np.mean(times))
+    return units / sec, sec, cores, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='hmmr', choices=['hmmr', 'single_frame', 'smpl'])
+    ap.add_argument('--clips', type=int, default=32, help='clips per GPU (hmmr) / frames per GPU x 1 (single_frame: 64)')
+    ap.add_argument('--mode', default=os.environ.get('HD_IMPL', 'tc3'), choices=['tc3', 'simt', 'tc1'],
+                    help='tc3 = tcgen05 3xTF32 (FP32-class parity mode, the headline); tc1 = single-pass TF32 (fails parity)')
+    ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '32')))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    unit_name = 'poses/sec' if args.workload == 'smpl' else 'frames/sec'
+    metric = 'frames/sec (ResNet->f_movie->SMPL LBS)' if args.workload == 'hmmr' else (
+        'frames/sec (ResNet->IEF->SMPL, single frame)' if args.workload == 'single_frame' else 'poses/sec (SMPL LBS)')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        v, sec, cores, sample = cpu_reference_run(args.workload, args.steps, args.warmup)
+        line = {'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit_name, 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(args), 'note': 'TF 1.8 cannot be installed here; restated reference on host CPU'},
+                'cpu_baseline': {'value': v, 'unit': unit_name, 'cores': cores, 'kind': 'port', 'sample': sample},
+                'e2e': {'value': v, 'unit': unit_name, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from human_dynamics_b200 import synthetic, HMMRConfig, _lib
+    from human_dynamics_b200.engine import HMMREngine
+    from human_dynamics_b200.dist import gather_outputs
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    peaks = load_peaks()
+    w = synthetic.make_synthetic_weights(seed=1)
+    smpl = synthetic.make_synthetic_smpl(seed=2)
+    T = 20
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == 'smpl':
+        from human_dynamics_b200.smpl import SMPLConstants
+        N = 65536
+        consts = SMPLConstants(smpl, device=dev)
+        beta, theta = synthetic.make_smpl_inputs(N, seed=rank)
+        b_d, t_d = torch.from_numpy(beta).to(dev), torch.from_numpy(theta).to(dev)
+        cam = torch.ones((N, 3), device=dev)
+        outs = consts.forward(b_d, t_d, cam=cam)
+
+        def step():
+            consts.forward(b_d, t_d, cam=cam, out=outs)
+        units_per_step, B = N, None
+        gather_keys = ()
+    else:
+        single = args.workload == 'single_frame'
+        B = 64 if single and args.clips == 32 else args.clips
+        Tw = 1 if single else T
+        cfg = HMMRConfig(batch_size=B, sequence_length=Tw, frame_chunk=args.frame_chunk)
+        eng = HMMREngine(w, smpl, cfg, device=dev, impl=args.mode)
+        img_host = torch.from_numpy(synthetic.make_images(B * Tw, seed=100 + rank)).view(B, Tw, 224, 224, 3).pin_memory()
+        img_dev = img_host.to(dev)
+        units_per_step = B * Tw
+        gather_keys = ('omegas', 'verts', 'kps')          # per-clip outputs named by BASELINE config 4 / SURVEY 8e
+        last = {}
+
+        def step():
+            out = eng.predict(img_dev, single_frame=single)
+            if world > 1:
+                last['g'] = gather_outputs({k: out[k] for k in gather_keys}, B * world, dst=0)
+
+        def step_e2e():
+            host, h2d, d2h = eng.predict_host(img_host, single_frame=single)
+            torch.cuda.current_stream().synchronize()
+            return h2d, d2h
+
+    # ------------------------------------------------------------------ device-resident timing (value)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.lib.hd_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = int(_lib.lib.hd_launch_count())
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = units_per_step * world / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ end-to-end through the public API (host buffers)
+    e2e = None
+    if args.workload != 'smpl':
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h2d, d2h = step_e2e()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / args.steps
+        if world > 1:
+            ts = torch.tensor([sec], device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            sec = float(ts.item())
+        e2e = {'value': units_per_step * world / sec, 'unit': unit_name, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': sec * 1e3, 'api': 'HMMREngine.predict_host (= Tester.predict on host arrays): pinned H2D in frame chunks '
+               'overlapped with ResNet, all 14 fetch tensors D2H'}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (instrumented extra pass)
+    roofline = None
+    if rank == 0:
+        roofline = measure_roofline(args, peaks, locals())
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores, sample = cpu_reference_run(args.workload, 2, 1)
+        cpu_baseline = {'value': v, 'unit': unit_name, 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        line = {'metric': metric, 'value': value, 'unit': unit_name, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32 (tcgen05 3xTF32 split, fp32 accumulate)' if args.mode == 'tc3' else ('f32' if args.mode == 'simt' else 'tf32'),
+                'data': 'synthetic',
+                'config': {'workload': workload_name(args), 'mode': args.mode, 'frame_chunk': args.frame_chunk,
+                           'l2': 'inputs larger than L2 (%.0f MB of frames per step vs 126 MB)' % (units_per_step * 224 * 224 * 3 * 4 / 1e6)
+                           if args.workload != 'smpl' else 'outputs larger than L2 (5.4 GB of vertices per step)',
+                           'parallelism': 'dp%d (clips sharded, gather of %s to rank 0)' % (world, '/'.join(gather_keys)) if world > 1 else 'single GPU',
+                           'peaks': peaks['source']},
+                'clocks': clocks, 'gpu_launches': launches,
+                'gpu_launches_per_step': launches / max(1, args.steps)}
+        if e2e:
+            line['e2e'] = e2e
+        if roofline:
+            line['roofline'] = roofline
+        if cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_name(args):
+    if args.workload == 'hmmr':
+        return 'BASELINE configs[2] (configs[3] per GPU at N=8): full HMMR, T=20 window, %d clips per GPU, 224x224x3' % args.clips
+    if args.workload == 'single_frame':
+        return 'BASELINE configs[1]: single-frame ResNet-50 + 3-iter IEF + SMPL, batch 64'
+    return 'BASELINE configs[4]: SMPL LBS microbench, 65536 poses -> 6890 verts'
+
+
+def measure_roofline(args, peaks, env):
+    """Instrumented extra pass (NOT part of `value`): CUDA events around every launch of the dominant kernel."""
+    import torch
+    if args.workload == 'smpl':
+        # one fused blend+skin kernel dominates: HBM-bound target
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step = env['step']
+        torch.cuda.synchronize()
+        e0.record(); step(); e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3
+        ach = 65536 * BYTES_SMPL_POSE / t / 1e9
+        return {'bound': 'hbm', 'kernel': 'smpl_pose + smpl_skin + smpl_joints (whole hd_smpl_forward)', 'achieved': ach,
+                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'], 'traffic': None,
+                'algorithmic_bytes_per_launch': 65536 * BYTES_SMPL_POSE}
+    eng, img_dev = env['eng'], env['img_dev']
+    single = args.workload == 'single_frame'
+    from human_dynamics_b200 import _lib
+    # time every conv-GEMM launch of one ResNet chunk pass with its own event pair
+    N = img_dev.shape[0] * img_dev.shape[1]
+    chunk = max(1, min(args.frame_chunk, N))
+    plan = eng._resnet_plan(chunk, 224)
+    phi = torch.empty((chunk, 2048), device=img_dev.device)
+    x = img_dev.reshape(N, 224, 224, 3)[:chunk]
+    st = torch.cuda.current_stream().cuda_stream
+    import ctypes
+    stp = ctypes.c_void_p(st)
+    plan.run(x, phi)
+    torch.cuda.synchronize()
+    evs = []
+    for op in plan.ops:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); op.run(stp); b.record()
+        evs.append((a, b, op))
+    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ta.record(); plan.run(x, phi); tb.record()
+    torch.cuda.synchronize()
+    tc_time, tc_flops, n_tc, all_time = 0.0, 0.0, 0, 0.0
+    for a, b, op in evs:
+        d = op.d
+        fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
+        t = a.elapsed_time(b) * 1e-3
+        all_time += t
+        if d.impl != _lib.HD_IMPL_SIMT:
+            tc_time += t; tc_flops += fl; n_tc += 1
+    kind = 'conv_gemm_tc_kernel (tcgen05 3xTF32 implicit GEMM)' if n_tc else 'conv_gemm_simt_kernel'
+    if n_tc == 0:
+        tc_time, tc_flops, n_tc = all_time, sum(2.0 * o.d.n_img * o.d.Ho * o.d.Wo * o.d.Cout * o.d.KH * o.d.KW * o.d.Cin for _, _, o in evs), len(evs)
+    ach = tc_flops / tc_time / 1e12
+    peak = peaks['bf16_tflops_sustained']
+    resnet_ms = ta.elapsed_time(tb)
+    return {'bound': 'tensor', 'kernel': kind, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+            'launches_timed': n_tc, 'avg_launch_us': tc_time / n_tc * 1e6, 'algorithmic_flops_per_launch_avg': tc_flops / n_tc,
+            'share_of_resnet_pass': tc_time / (resnet_ms * 1e-3),
+            'note': 'algorithmic FLOPs (2*M*N*K, dense, as the reference computes them) of the %d tensor-core conv launches of one '
+                    '%d-frame ResNet pass / their summed CUDA-event durations; peak = bf16 dense sustained (%s). The parity mode issues '
+                    '3 TF32 MMAs per product (TF32 runs at half the bf16 rate), so its ceiling is 1/6 of this peak.' % (n_tc, chunk, peaks['source'])}
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -4,14 +4,21 @@
 //
 // A (activations) never exists in HBM in im2col form: four producer warps gather the 128 x 32 fp32 tile
 // (zero padding, stride, per-channel BN/GN affine + ReLU prologue fused), split every value into its
-// TF32-exact head `hi` (low 13 mantissa bits cleared -- exactly what the tensor core would read) and the
+// TF32-exact head `hi` (rounded to nearest; low 13 mantissa bits clear -- all the tensor core reads) and the
 // fp32 remainder `lo = x - hi`, and store both straight into the 128-byte-swizzled K-major layout that the
 // UMMA shared-memory descriptor expects.  B (weights, pre-split offline into hi/lo, K-major) arrives by TMA.
 // One elected thread issues tcgen05.mma.kind::tf32; accumulators live in TMEM and are read back with
 // tcgen05.ld for the fused epilogue (per-channel scale/shift, residual add, ReLU).
 //
-// Warp roles (192 threads):  0-3 A producers, then epilogue (TMEM lane quarter = warp id);
-//                            4   TMEM allocator + TMA producer for B;   5   MMA issuer.
+// Accumulation precision: the tensor core TRUNCATES the fp32 accumulator on every MMA (measured: relative
+// error ~2.7e-8 per accumulation, growing linearly with K; 1.4e-4 at K=16384), which is not FP32-class.
+// So accumulation is two-level: the dominant A_hi*B_hi term is summed in TMEM for only PCH K-chunks
+// (4*PCH MMAs) into one of two ping-pong accumulators, which four drain warps then add -- round-to-nearest,
+// on the CUDA cores -- into per-thread fp32 running sums while the MMA warp fills the other accumulator.
+// The two cross terms (2^-11 smaller) accumulate in a third TMEM region for the whole K loop.
+//
+// Warp roles (320 threads):  0-3 drain + epilogue (TMEM lane quarter = warp id);  4-7 A producers;
+//                            8   TMEM allocator + TMA producer for B;             9   MMA issuer.
 #include <cuda.h>
 #include "conv_common.cuh"
 
@@ -20,7 +27,7 @@ namespace {
 
 constexpr int BM = 128, BK = 32, STAGES = 3;
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,6 +78,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Nearest value with the low 13 mantissa bits clear (all the tf32 datapath reads).
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -88,11 +98,12 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;   // + barriers + alignment slack
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;      // cross-term accumulator + two ping-pong accumulators
   // kind::tf32, D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int PCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
   using C = Cfg<BN>;
@@ -102,8 +113,9 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   const uint32_t bar_base = smem_base + C::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 1));
+  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };       // accumulator b ready to drain
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };   // accumulator b drained
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -114,21 +126,26 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       mbar_init(full_bar(s), 5);     // 4 producer warps + 1 arrive.expect_tx from the TMA lane
       mbar_init(empty_bar(s), 1);    // tcgen05.commit
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar(b), 1);     // tcgen05.commit
+      mbar_init(acce_bar(b), 4);     // one lane per drain warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(BN));
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_small = tmem_d;                 // cross terms A_lo*B_hi + A_hi*B_lo
+  const int num_g = (num_k + PCH - 1) / PCH;          // drain groups
 
-  if (warp < 4) {
+  if (warp >= 4 && warp < 8) {
     // =============================== A producers ===============================
-    const int t = threadIdx.x;            // 0..127
+    const int t = threadIdx.x - 128;      // 0..127
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
     const int rb = t >> 3;                // rows rb + 16*i
     const uint32_t sw_off = (uint32_t)((j ^ (rb & 7)) << 4);
@@ -199,13 +216,12 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       for (int i = 0; i < 8; ++i) {
         const uint32_t off = (uint32_t)(rb + 16 * i) * 128u + sw_off;
         const float4 v = cur[i];
-        float4 hi;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        float4 hi;      // round-to-nearest TF32 head (zero-mean error), exact remainder, remainder rounded to TF32
+        hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
         *reinterpret_cast<float4 *>(a_hi + off) = hi;
-        if (SPLIT) *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        if (SPLIT)
+          *reinterpret_cast<float4 *>(a_lo + off) =
+              make_float4(rn_tf32(v.x - hi.x), rn_tf32(v.y - hi.y), rn_tf32(v.z - hi.z), rn_tf32(v.w - hi.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async proxy)
       __syncwarp();
@@ -215,9 +231,36 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       vmask_cur = vmask_nxt;
     }
 
-    // =============================== epilogue ===============================
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  } else if (warp < 4) {
+    // =============================== drain + epilogue ===============================
+    float sums[BN];
+#pragma unroll
+    for (int i = 0; i < BN; ++i) sums[i] = 0.f;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int g = 0; g < num_g; ++g) {
+      const int b = g & 1;
+      mbar_wait(accf_bar(b), (uint32_t)(g >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * (1 + b) + c0), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(b));
+    }
+    if (SPLIT) {      // the last accf commit also covers every cross-term MMA
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_small + lane_off + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);
+      }
+    }
     const int m = m0 + warp * 32 + lane;
     const bool mvalid = m < p.M;
     size_t res_row = 0;
@@ -228,18 +271,14 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       const int oy = r / p.Wo, ox = r - oy * p.Wo;
       res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
     }
-#pragma unroll 1
+#pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);   // whole warp: .sync.aligned
       if (!mvalid) continue;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int co = n0 + c0 + q * 4;
-        if (co >= p.Cout) break;
-        float x[4] = {__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                      __uint_as_float(v[q * 4 + 3])};
+        if (co >= p.Cout) continue;
+        float x[4] = {sums[c0 + q * 4 + 0], sums[c0 + q * 4 + 1], sums[c0 + q * 4 + 2], sums[c0 + q * 4 + 3]};
         if (p.vec_out) {
           if (p.post_scale) {
             const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.post_scale + co));
@@ -270,7 +309,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =============================== B producer (TMA) ===============================
     if (lane == 0) {
       for (int kc = 0; kc < num_k; ++kc) {
@@ -289,8 +328,12 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       for (int kc = 0; kc < num_k; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        const int g = kc / PCH, b = g & 1;
+        const bool group_start = (kc % PCH) == 0;
+        if (group_start) mbar_wait(acce_bar(b), ((uint32_t)(g >> 1) & 1u) ^ 1u);    // accumulator b drained
         mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_big = tmem_d + (uint32_t)(BN * (1 + b));
         const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
         const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
@@ -301,22 +344,20 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         for (int k = 0; k < BK / 8; ++k) {           // UMMA K = 8 for tf32 -> advance 32 bytes inside the swizzle atom
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
           if (SPLIT) {
-            umma_tf32(tmem_d, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);   // small terms first
-            umma_tf32(tmem_d, da_hi + adv, db_lo + adv, C::IDESC, 1u);
-            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, C::IDESC, 1u);
-          } else {
-            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+            umma_tf32(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+            umma_tf32(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
           }
+          umma_tf32(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
         }
         umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
+        if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
       }
-      umma_commit(tmem_full_bar);                    // accumulator complete -> epilogue
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(C::TMEM_COLS));
   }
 }
 
@@ -338,12 +379,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int PCH>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
     configured = true;
   }
@@ -351,7 +392,7 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   memcpy(&thi, d->tmap_hi, sizeof(CUtensorMap));
   memcpy(&tlo, d->tmap_lo ? d->tmap_lo : d->tmap_hi, sizeof(CUtensorMap));
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, BN));
-  conv_gemm_tc_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  conv_gemm_tc_kernel<BN, SPLIT, PCH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -368,8 +409,9 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
     return HD_ERR_INVALID;
   }
   const bool split = d->impl == HD_IMPL_TC_3XTF32;
-  if (p.Cout <= 64) return split ? launch_tc<64, true>(p, d, st) : launch_tc<64, false>(p, d, st);
-  return split ? launch_tc<128, true>(p, d, st) : launch_tc<128, false>(p, d, st);
+  // 3xTF32: drain every chunk (3 truncating accumulations per drained value); 1xTF32 is ~1e-3 anyway: drain rarely
+  if (p.Cout <= 64) return split ? launch_tc<64, true, 1>(p, d, st) : launch_tc<64, false, 8>(p, d, st);
+  return split ? launch_tc<128, true, 1>(p, d, st) : launch_tc<128, false, 8>(p, d, st);
 }
 
 }  // namespace hd

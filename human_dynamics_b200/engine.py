@@ -157,6 +157,59 @@ class HMMREngine(object):
         phi = self.encode_images(images.reshape((N,) + tuple(images.shape[2:])), out=self._phi[key])
         return self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
 
+    FETCH_KEYS = tuple(a + b for b in ('', '_delta') for a in ('cams', 'joints', 'kps', 'poses', 'shapes', 'verts', 'omegas'))
+
+    def predict_host(self, images_host, single_frame=False, fetch=None):
+        """The one host->device->host crossing of `sess.run(fetch_dict, feed_dict)` (tester.py:239-258).
+
+        images_host: (B,T,S,S,3) float32 CPU tensor (pinned for real overlap).  Frames go up in `frame_chunk`
+        pieces on a copy stream while the ResNet consumes earlier pieces; results come back into pinned host
+        buffers owned by the engine.  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes); the copies are only
+        complete after `torch.cuda.current_stream().synchronize()`.
+        """
+        if images_host.is_cuda or images_host.dtype != torch.float32 or images_host.dim() != 5:
+            raise _lib.HDError('predict_host: expected a float32 CPU tensor (B,T,S,S,3)')
+        B, T, S = images_host.shape[0], images_host.shape[1], images_host.shape[2]
+        N = B * T
+        flat = images_host.reshape(N, S, S, 3)
+        key = ('img', N, S)
+        if key not in self._phi:
+            self._phi[key] = torch.empty((N, S, S, 3), dtype=torch.float32, device=self.device)
+            self._phi[('phi', N)] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
+            self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
+        dev_img, phi = self._phi[key], self._phi[('phi', N)]
+        chunk = max(1, min(int(self.config.frame_chunk), N))
+        starts = list(range(0, N, chunk))
+        ekey = ('ev', len(starts))
+        if ekey not in self._phi:
+            self._phi[ekey] = [torch.cuda.Event() for _ in starts]
+        events = self._phi[ekey]
+        main = torch.cuda.current_stream()
+        cs = self._copy_stream
+        cs.wait_stream(main)                         # the previous step may still read dev_img
+        with torch.cuda.stream(cs):
+            for ev, i in zip(events, starts):
+                n = min(chunk, N - i)
+                dev_img[i:i + n].copy_(flat[i:i + n], non_blocking=True)
+                ev.record(cs)
+        st = current_stream()
+        for ev, i in zip(events, starts):
+            n = min(chunk, N - i)
+            main.wait_event(ev)
+            self._resnet_plan(n, S).run(dev_img[i:i + n], phi[i:i + n], st)
+        out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
+        keys = [k for k in (fetch or self.FETCH_KEYS) if k in out]
+        host, d2h = {}, 0
+        for k in keys:
+            v = out[k]
+            hk = ('host', k, tuple(v.shape))
+            if hk not in self._phi:
+                self._phi[hk] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
+            self._phi[hk].copy_(v, non_blocking=True)
+            host[k] = self._phi[hk]
+            d2h += v.numel() * 4
+        return host, flat.numel() * 4, d2h
+
     def predict_from_features(self, phi, single_frame=False):
         B, T = phi.shape[0], phi.shape[1]
         N = B * T

@@ -36,10 +36,15 @@ def fold_bn(w, prefix):
 
 
 def tf32_split(w):
-    """w (float32) -> (hi, lo): hi has the low 13 mantissa bits cleared (what the tensor core reads), lo = w - hi."""
-    bits = w.view(np.uint32) & np.uint32(0xFFFFE000)
-    hi = bits.view(np.float32)
-    lo = (w - hi).astype(np.float32)
+    """w (float32) -> (hi, lo), both exactly representable in TF32 (low 13 mantissa bits zero, which is all the
+    tensor core reads): hi = w rounded to nearest TF32, lo = (w - hi) rounded to nearest TF32.  Rounding (not
+    truncating) keeps the representation error zero-mean, so it does not build up over the 53 layers."""
+    def rn_tf32(x):
+        b = np.ascontiguousarray(x, np.float32).view(np.uint32)
+        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    hi = rn_tf32(w)
+    lo = rn_tf32((w - hi).astype(np.float32))
     return hi, lo
 
 

@@ -51,28 +51,25 @@ class Tester(object):
         if tuple(images.shape) != exp:
             raise ValueError('images must have the static shape %s baked at construction (tester.py:64-66), got %s'
                              % (exp, tuple(images.shape)))
-        dev = self.engine.device
         if isinstance(images, np.ndarray):
             images = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
-        if not images.is_cuda:
-            images = images.to(dev, dtype=torch.float32, non_blocking=True)
-        out = self.engine.predict(images.float())
-        out = {k: v for k, v in out.items() if not k.startswith('_')}
-        if not as_numpy:
-            return out
-        return self._fetch(out)
-
-    def _fetch(self, out):
-        """Device -> pinned host -> numpy: the result half of the one host<->device crossing (tester.py:257)."""
-        res = {}
-        for k, v in out.items():
-            key = (k, tuple(v.shape))
-            if key not in self._pinned:
-                self._pinned[key] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
-            self._pinned[key].copy_(v, non_blocking=True)
-            res[k] = self._pinned[key]
+        if images.is_cuda:
+            out = self.engine.predict(images.float())
+            out = {k: v for k, v in out.items() if not k.startswith('_')}
+            if not as_numpy:
+                return out
+            torch.cuda.current_stream().synchronize()
+            return {k: v.cpu().numpy() for k, v in out.items()}
+        # host input: one overlapped host->device->host crossing, like sess.run(fetch_dict, feed_dict) (tester.py:257)
+        key = tuple(images.shape)
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(key, dtype=torch.float32, pin_memory=True)
+        self._pinned[key].copy_(images)
+        host, _, _ = self.engine.predict_host(self._pinned[key])
         torch.cuda.current_stream().synchronize()
-        return {k: v.numpy().copy() for k, v in res.items()}
+        if not as_numpy:
+            return host
+        return {k: v.numpy().copy() for k, v in host.items()}
 
     def predict_all_images(self, all_images):
         """Sliding-window prediction over a whole sequence (tester.py:260-312).  all_images: N x H x W x 3."""
