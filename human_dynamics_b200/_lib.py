@@ -53,6 +53,7 @@ SIGNATURES = {
     'hd_launch_count': (_ll, []),
     'hd_launch_count_reset': (None, []),
     'hd_conv_gemm': (_i, [C.POINTER(ConvDesc), _vp]),
+    'hd_conv_gemm_profile': (_i, [C.POINTER(ConvDesc), _vp, _vp]),
     'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

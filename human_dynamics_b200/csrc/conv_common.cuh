@@ -14,6 +14,7 @@ struct ConvParams {
   float *out; long long out_ld;
   int vec_out;   // out/res/post vectors allow float4 access
   int K_pad;     // tensor-core path: padded K of the packed weights
+  long long *dbg;  // optional: per-role cycle counters of CTA (0,0) (hd_conv_gemm_profile), else nullptr
 };
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -48,6 +49,7 @@ inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
               (!d->res || ((d->res_ld % 4 == 0) && aligned16(d->res))) &&
               (!d->post_scale || aligned16(d->post_scale)) && (!d->post_shift || aligned16(d->post_shift));
   p.K_pad = d->K_pad;
+  p.dbg = nullptr;
   return HD_OK;
 }
 

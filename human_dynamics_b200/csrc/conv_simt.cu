@@ -232,13 +232,21 @@ int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
 
 }  // namespace hd
 
-extern "C" int hd_conv_gemm(const hd_conv_desc *d, void *stream) {
+static int conv_gemm_impl(const hd_conv_desc *d, void *stream, long long *dbg) {
   hd::ConvParams p;
   int rc = hd::fill_params(d, p);
   if (rc) return rc;
+  p.dbg = dbg;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->impl == HD_IMPL_SIMT) return hd::launch_conv_simt(p, st);
   if (d->impl == HD_IMPL_TC_3XTF32 || d->impl == HD_IMPL_TC_1XTF32) return hd::launch_conv_tc(p, d, st);
   hd::set_last_error_text("hd_conv_gemm: unknown impl");
   return HD_ERR_INVALID;
 }
+
+extern "C" int hd_conv_gemm(const hd_conv_desc *d, void *stream) { return conv_gemm_impl(d, stream, nullptr); }
+
+// Same launch, but CTA (0,0) of the tensor-core kernel writes per-role cycle counters to dbg[0..15] (device int64):
+// [0] producer loop, [1] producer wait-empty, [2] drain loop, [3] drain wait-accf, [4] epilogue,
+// [5] MMA loop, [6] MMA wait-full, [7] MMA wait-acc-drained, [8] TMA loop, [9] TMA wait-empty.
+extern "C" int hd_conv_gemm_profile(const hd_conv_desc *d, void *stream, long long *dbg) { return conv_gemm_impl(d, stream, dbg); }

@@ -97,7 +97,11 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;   // + barriers + alignment slack
+  static constexpr int STG_LD = BN + 4;                          // padded row of the epilogue staging tile (floats)
+  static constexpr int STG_ROWS = 8;                            // rows staged per warp per pass
+  static constexpr int STG_OFFSET = BAR_OFFSET + 128;
+  static constexpr int STG_BYTES = 4 * STG_ROWS * STG_LD * 4;   // 4 drain warps
+  static constexpr int SMEM_BYTES = STG_OFFSET + STG_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;      // cross-term accumulator + two ping-pong accumulators
   // kind::tf32, D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -182,6 +186,8 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
     };
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0;
+    long long t_wait = 0, t_start = prof ? clock64() : 0;
     if (num_k > 0) gather(0, cur, vmask_cur);
     for (int kc = 0; kc < num_k; ++kc) {
       const int s = kc % STAGES;
@@ -209,7 +215,9 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           cur[i] = v;
         }
       }
+      long long tw0 = prof ? clock64() : 0;
       mbar_wait(empty_bar(s), ph ^ 1u);
+      if (prof) t_wait += clock64() - tw0;
       uint8_t *a_hi = smem + s * C::STAGE_BYTES;
       uint8_t *a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
@@ -230,6 +238,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       vmask_cur = vmask_nxt;
     }
+    if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
 
   } else if (warp < 4) {
     // =============================== drain + epilogue ===============================
@@ -237,9 +246,13 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
     for (int i = 0; i < BN; ++i) sums[i] = 0.f;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    long long t_wait = 0, t_start = prof ? clock64() : 0;
     for (int g = 0; g < num_g; ++g) {
       const int b = g & 1;
+      long long tw0 = prof ? clock64() : 0;
       mbar_wait(accf_bar(b), (uint32_t)(g >> 1) & 1u);
+      if (prof) t_wait += clock64() - tw0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -261,46 +274,86 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);
       }
     }
-    const int m = m0 + warp * 32 + lane;
-    const bool mvalid = m < p.M;
-    size_t res_row = 0;
-    if (p.res && mvalid) {
-      const int hw = p.Ho * p.Wo;
-      const int n = m / hw;
-      const int r = m - n * hw;
-      const int oy = r / p.Wo, ox = r - oy * p.Wo;
-      res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+    long long t_epi0 = 0;
+    if (prof) { t_epi0 = clock64(); p.dbg[2] = t_epi0 - t_start; p.dbg[3] = t_wait; }
+    // Epilogue.  Each lane owns one accumulator ROW (TMEM lane), but global memory wants a warp to touch one
+    // row's contiguous columns at a time: transpose through a small padded smem tile, 8 rows per pass, then
+    // every warp-level access below is BN*4 contiguous bytes (residual load, output store).
+    float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::STG_ROWS * C::STG_LD);
+    constexpr int CPL = BN / 32;                 // consecutive columns per lane in the coalesced phase (4 or 2)
+    const int col = lane * CPL;
+    const int co = n0 + col;
+    const bool cvalid = co < p.Cout;             // Cout % CPL == 0 is guaranteed by vec_out; ragged Cout takes the scalar path
+    float psc[CPL], psh[CPL];
+#pragma unroll
+    for (int e = 0; e < CPL; ++e) {
+      psc[e] = (p.post_scale && co + e < p.Cout) ? __ldg(p.post_scale + co + e) : 1.0f;
+      psh[e] = (p.post_shift && co + e < p.Cout) ? __ldg(p.post_shift + co + e) : 0.0f;
     }
+    const int hw = p.Ho * p.Wo;
 #pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (!mvalid) continue;
+    for (int pass = 0; pass < 32 / C::STG_ROWS; ++pass) {
+      __syncwarp();
+      if ((lane / C::STG_ROWS) == pass) {        // the 8 lanes whose rows are staged in this pass
+        float *dst = stg + (lane % C::STG_ROWS) * C::STG_LD;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int co = n0 + c0 + q * 4;
-        if (co >= p.Cout) continue;
-        float x[4] = {sums[c0 + q * 4 + 0], sums[c0 + q * 4 + 1], sums[c0 + q * 4 + 2], sums[c0 + q * 4 + 3]};
+        for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(sums[c], sums[c + 1], sums[c + 2], sums[c + 3]);
+      }
+      __syncwarp();
+      // residual rows of this pass first (8 independent coalesced loads in flight), then the math and the stores
+      float rres[C::STG_ROWS][CPL];
+      if (p.res && p.vec_out && cvalid) {
+#pragma unroll
+        for (int r = 0; r < C::STG_ROWS; ++r) {
+          const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
+#pragma unroll
+          for (int e = 0; e < CPL; ++e) rres[r][e] = 0.f;
+          if (m < p.M) {
+            const int n = m / hw;
+            const int rr = m - n * hw;
+            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+            const float *rp = p.res + (((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride) * p.res_ld + co;
+            if (CPL == 4) {
+              const float4 rv = __ldg(reinterpret_cast<const float4 *>(rp));
+              rres[r][0] = rv.x; rres[r][1] = rv.y; rres[r][CPL - 2] = rv.z; rres[r][CPL - 1] = rv.w;
+            } else {
+              const float2 rv = __ldg(reinterpret_cast<const float2 *>(rp));
+              rres[r][0] = rv.x; rres[r][1] = rv.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < C::STG_ROWS; ++r) {
+        const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
+        if (m >= p.M) break;                     // warp-uniform
+        float x[CPL];
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) x[e] = stg[r * C::STG_LD + col + e] * psc[e] + psh[e];
+        if (!cvalid) continue;
         if (p.vec_out) {
-          if (p.post_scale) {
-            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.post_scale + co));
-            x[0] *= sc.x; x[1] *= sc.y; x[2] *= sc.z; x[3] *= sc.w;
-          }
-          if (p.post_shift) {
-            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.post_shift + co));
-            x[0] += sh.x; x[1] += sh.y; x[2] += sh.z; x[3] += sh.w;
-          }
           if (p.res) {
-            const float4 r = *reinterpret_cast<const float4 *>(p.res + res_row * p.res_ld + co);
-            x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
-          }
-          if (p.post_relu) { x[0] = fmaxf(x[0], 0.f); x[1] = fmaxf(x[1], 0.f); x[2] = fmaxf(x[2], 0.f); x[3] = fmaxf(x[3], 0.f); }
-          *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < CPL; ++e) x[e] += rres[r][e];
+          }
+          if (p.post_relu) {
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) x[e] = fmaxf(x[e], 0.f);
+          }
+          if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
+          else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
+        } else {
+          size_t res_row = 0;
+          if (p.res) {
+            const int n = m / hw;
+            const int rr = m - n * hw;
+            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+            res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+          }
+#pragma unroll
+          for (int e = 0; e < CPL; ++e) {
             if (co + e >= p.Cout) continue;
             float y = x[e];
-            if (p.post_scale) y *= __ldg(p.post_scale + co + e);
-            if (p.post_shift) y += __ldg(p.post_shift + co + e);
             if (p.res) y += p.res[res_row * p.res_ld + co + e];
             if (p.post_relu) y = fmaxf(y, 0.f);
             p.out[(size_t)m * p.out_ld + co + e] = y;
@@ -308,30 +361,41 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
     }
+    if (prof) p.dbg[4] = clock64() - t_epi0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (warp == 8) {
     // =============================== B producer (TMA) ===============================
     if (lane == 0) {
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      long long t_wait = 0, t_start = prof ? clock64() : 0;
       for (int kc = 0; kc < num_k; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        long long tw0 = prof ? clock64() : 0;
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if (prof) t_wait += clock64() - tw0;
         const uint32_t b_hi = smem_base + s * C::STAGE_BYTES + 2 * A_TILE_BYTES;
         mbar_arrive_expect_tx(full_bar(s), SPLIT ? 2 * C::B_TILE_BYTES : C::B_TILE_BYTES);
         tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BK, n0);
         if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BK, n0);
       }
+      if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
     }
   } else {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      long long t_wfull = 0, t_wacc = 0, t_start = prof ? clock64() : 0;
       for (int kc = 0; kc < num_k; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
         const int g = kc / PCH, b = g & 1;
         const bool group_start = (kc % PCH) == 0;
+        long long tw0 = prof ? clock64() : 0;
         if (group_start) mbar_wait(acce_bar(b), ((uint32_t)(g >> 1) & 1u) ^ 1u);    // accumulator b drained
+        long long tw1 = prof ? clock64() : 0;
         mbar_wait(full_bar(s), ph);
+        if (prof) { t_wacc += tw1 - tw0; t_wfull += clock64() - tw1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_big = tmem_d + (uint32_t)(BN * (1 + b));
         const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
@@ -352,6 +416,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
         if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
       }
+      if (prof) { p.dbg[5] = clock64() - t_start; p.dbg[6] = t_wfull; p.dbg[7] = t_wacc; }
     }
   }
   __syncthreads();
@@ -409,9 +474,10 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
     return HD_ERR_INVALID;
   }
   const bool split = d->impl == HD_IMPL_TC_3XTF32;
-  // 3xTF32: drain every chunk (3 truncating accumulations per drained value); 1xTF32 is ~1e-3 anyway: drain rarely
-  if (p.Cout <= 64) return split ? launch_tc<64, true, 1>(p, d, st) : launch_tc<64, false, 8>(p, d, st);
-  return split ? launch_tc<128, true, 1>(p, d, st) : launch_tc<128, false, 8>(p, d, st);
+  // 3xTF32: drain every 4 chunks = 16 truncating accumulations (~4e-7 relative, below fp32 SIMT summation noise);
+  // 1xTF32 is ~1e-3 anyway: drain rarely
+  if (p.Cout <= 64) return split ? launch_tc<64, true, 4>(p, d, st) : launch_tc<64, false, 8>(p, d, st);
+  return split ? launch_tc<128, true, 4>(p, d, st) : launch_tc<128, false, 8>(p, d, st);
 }
 
 }  // namespace hd

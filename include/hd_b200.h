@@ -72,6 +72,9 @@ typedef struct {
 } hd_conv_desc;
 
 int hd_conv_gemm(const hd_conv_desc *d, void *stream);
+/* Same launch; additionally CTA (0,0) of the tensor-core kernel writes per-role clock64 counters to dbg[0..15]
+ * (device int64; layout in conv_simt.cu).  Tuning aid, not part of the reference surface. */
+int hd_conv_gemm_profile(const hd_conv_desc *d, void *stream, long long *dbg);
 
 /* Encode the TMA descriptor (CUtensorMap, 128 B, written to host memory `tmap_out`) for a K-major
  * weight matrix [rows, k_pad] fp32 with a {32 x box_rows} box and 128-byte swizzle. */
