@@ -145,7 +145,8 @@ def main():
     ap.add_argument('--clips', type=int, default=32, help='clips per GPU (hmmr) / frames per GPU x 1 (single_frame: 64)')
     ap.add_argument('--mode', default=os.environ.get('HD_IMPL', 'tc3'), choices=['tc3', 'simt', 'tc1'],
                     help='tc3 = tcgen05 3xTF32 (FP32-class parity mode, the headline); tc1 = single-pass TF32 (fails parity)')
-    ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '32')))
+    ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '64')))
+    ap.add_argument('--late-chunk', type=int, default=int(os.environ.get('HD_LATE_CHUNK', '640')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
@@ -209,7 +210,7 @@ def main():
         single = args.workload == 'single_frame'
         B = 64 if single and args.clips == 32 else args.clips
         Tw = 1 if single else T
-        cfg = HMMRConfig(batch_size=B, sequence_length=Tw, frame_chunk=args.frame_chunk)
+        cfg = HMMRConfig(batch_size=B, sequence_length=Tw, frame_chunk=args.frame_chunk, late_chunk=args.late_chunk)
         eng = HMMREngine(w, smpl, cfg, device=dev, impl=args.mode)
         img_host = torch.from_numpy(synthetic.make_images(B * Tw, seed=100 + rank)).view(B, Tw, 224, 224, 3).pin_memory()
         img_dev = img_host.to(dev)
@@ -284,7 +285,7 @@ def main():
                 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32 (tcgen05 3xTF32 split, fp32 accumulate)' if args.mode == 'tc3' else ('f32' if args.mode == 'simt' else 'tf32'),
                 'data': 'synthetic',
-                'config': {'workload': workload_name(args), 'mode': args.mode, 'frame_chunk': args.frame_chunk,
+                'config': {'workload': workload_name(args), 'mode': args.mode, 'frame_chunk': args.frame_chunk, 'late_chunk': args.late_chunk,
                            'l2': 'inputs larger than L2 (%.0f MB of frames per step vs 126 MB)' % (units_per_step * 224 * 224 * 3 * 4 / 1e6)
                            if args.workload != 'smpl' else 'outputs larger than L2 (5.4 GB of vertices per step)',
                            'parallelism': 'dp%d (clips sharded, gather of %s to rank 0)' % (world, '/'.join(gather_keys)) if world > 1 else 'single GPU',
@@ -326,48 +327,42 @@ def measure_roofline(args, peaks, env):
                 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'], 'traffic': None,
                 'algorithmic_bytes_per_launch': 65536 * BYTES_SMPL_POSE}
     eng, img_dev = env['eng'], env['img_dev']
-    single = args.workload == 'single_frame'
     from human_dynamics_b200 import _lib
-    # time every conv-GEMM launch of one ResNet chunk pass with its own event pair
-    N = img_dev.shape[0] * img_dev.shape[1]
-    chunk = max(1, min(args.frame_chunk, N))
-    plan = eng._resnet_plan(chunk, 224)
-    phi = torch.empty((chunk, 2048), device=img_dev.device)
-    x = img_dev.reshape(N, 224, 224, 3)[:chunk]
-    st = torch.cuda.current_stream().cuda_stream
     import ctypes
-    stp = ctypes.c_void_p(st)
-    plan.run(x, phi)
-    torch.cuda.synchronize()
-    evs = []
-    for op in plan.ops:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); op.run(stp); b.record()
-        evs.append((a, b, op))
-    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ta.record(); plan.run(x, phi); tb.record()
-    torch.cuda.synchronize()
-    tc_time, tc_flops, n_tc, all_time = 0.0, 0.0, 0, 0.0
-    for a, b, op in evs:
-        d = op.d
-        fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
-        t = a.elapsed_time(b) * 1e-3
-        all_time += t
-        if d.impl != _lib.HD_IMPL_SIMT:
-            tc_time += t; tc_flops += fl; n_tc += 1
-    kind = 'conv_gemm_tc_kernel (tcgen05 3xTF32 implicit GEMM)' if n_tc else 'conv_gemm_simt_kernel'
-    if n_tc == 0:
-        tc_time, tc_flops, n_tc = all_time, sum(2.0 * o.d.n_img * o.d.Ho * o.d.Wo * o.d.Cout * o.d.KH * o.d.KW * o.d.Cin for _, _, o in evs), len(evs)
+    N = img_dev.shape[0] * img_dev.shape[1]
+    cA = max(1, min(int(eng.config.frame_chunk), N))
+    cB = max(1, min(int(eng.config.late_chunk), N))
+    stp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    tc_time, tc_flops, n_tc, conv_time = 0.0, 0.0, 0, 0.0
+    # one chunk pass of each trunk stage with an event pair around every conv launch (plans are bound by the timed steps)
+    for stage, c in (('A', cA), ('B', cB)):
+        plan = eng._resnet_plan(c, 224, stage)
+        reps = N // c
+        evs = []
+        torch.cuda.synchronize()
+        for op in plan.ops:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); op.run(stp); b.record()
+            evs.append((a, b, op))
+        torch.cuda.synchronize()
+        for a, b, op in evs:
+            d = op.d
+            fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
+            t = a.elapsed_time(b) * 1e-3
+            conv_time += t * reps
+            if d.impl != _lib.HD_IMPL_SIMT or args.mode == 'simt':
+                tc_time += t * reps; tc_flops += fl * reps; n_tc += reps
+    kind = 'conv_gemm_tc_kernel (tcgen05 3xTF32 implicit GEMM, persistent)' if args.mode != 'simt' else 'conv_gemm_simt_kernel'
     ach = tc_flops / tc_time / 1e12
     peak = peaks['bf16_tflops_sustained']
-    resnet_ms = ta.elapsed_time(tb)
+    step_s = env['ms'] * 1e-3
     return {'bound': 'tensor', 'kernel': kind, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
-            'launches_timed': n_tc, 'avg_launch_us': tc_time / n_tc * 1e6, 'algorithmic_flops_per_launch_avg': tc_flops / n_tc,
-            'share_of_resnet_pass': tc_time / (resnet_ms * 1e-3),
-            'note': 'algorithmic FLOPs (2*M*N*K, dense, as the reference computes them) of the %d tensor-core conv launches of one '
-                    '%d-frame ResNet pass / their summed CUDA-event durations; peak = bf16 dense sustained (%s). The parity mode issues '
-                    '3 TF32 MMAs per product (TF32 runs at half the bf16 rate), so its ceiling is 1/6 of this peak.' % (n_tc, chunk, peaks['source'])}
+            'launches_per_step': n_tc, 'avg_launch_us': tc_time / n_tc * 1e6, 'algorithmic_flops_per_launch_avg': tc_flops / n_tc,
+            'share_of_step': tc_time / step_s,
+            'note': 'algorithmic FLOPs (2*M*N*K, dense, as the reference computes them) of the %d conv launches of one step / their '
+                    'CUDA-event durations (instrumented extra pass: one chunk of each trunk stage, scaled by its repeat count); '
+                    'peak = bf16 dense sustained (%s). The parity mode issues 3 TF32 MMAs per product and TF32 runs at half the '
+                    'bf16 rate, so its ceiling is 1/6 of this peak (%.0f TFLOP/s).' % (n_tc, peaks['source'], peak / 6)}
 
 
 if __name__ == '__main__':

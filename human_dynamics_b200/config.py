@@ -28,5 +28,6 @@ class HMMRConfig(object):
     weights: Any = None
     smpl_model: Any = None
     impl: str = os.environ.get('HD_IMPL', 'simt')   # 'auto' | 'simt' | 'tc3' | 'tc1'
-    frame_chunk: int = 32         # frames per ResNet pass (activation working set vs. L2)
+    frame_chunk: int = 64         # frames per pass of ResNet root + blocks 1-2 (activation working set vs. L2)
+    late_chunk: int = 640         # frames per pass of ResNet blocks 3-4 (small maps: batch wide to fill 148 SMs)
     extra: dict = field(default_factory=dict)

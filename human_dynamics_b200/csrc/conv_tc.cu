@@ -1,24 +1,30 @@
 // tcgen05 implicit-GEMM convolution / FC for sm_100a with FP32-class accuracy via 3xTF32 error compensation.
 //
-//   D[128 x BN] (fp32, TMEM)  +=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        per 32-wide K chunk
+//   D[128 x BN] (fp32)  =  sum over 32-wide K chunks of   A_hi*B_hi  +  (A_lo*B_hi + A_hi*B_lo)
 //
-// A (activations) never exists in HBM in im2col form: four producer warps gather the 128 x 32 fp32 tile
-// (zero padding, stride, per-channel BN/GN affine + ReLU prologue fused), split every value into its
-// TF32-exact head `hi` (rounded to nearest; low 13 mantissa bits clear -- all the tensor core reads) and the
-// fp32 remainder `lo = x - hi`, and store both straight into the 128-byte-swizzled K-major layout that the
-// UMMA shared-memory descriptor expects.  B (weights, pre-split offline into hi/lo, K-major) arrives by TMA.
-// One elected thread issues tcgen05.mma.kind::tf32; accumulators live in TMEM and are read back with
-// tcgen05.ld for the fused epilogue (per-channel scale/shift, residual add, ReLU).
+// A (activations) never exists in HBM in im2col form: eight producer warps gather the 128 x 32 fp32 tile
+// (zero padding, stride, per-channel BN/GN affine + ReLU prologue fused; three chunks of loads in flight per
+// thread), split every value into its TF32-exact head `hi` (rounded to nearest; low 13 mantissa bits clear --
+// all the tensor core reads) and the remainder `lo = x - hi`, and store both straight into the 128-byte-swizzled
+// K-major layout the UMMA shared-memory descriptor expects.  B (weights, pre-split offline into hi/lo, K-major)
+// arrives by TMA.  One elected thread issues tcgen05.mma.kind::tf32; accumulators live in TMEM.
 //
 // Accumulation precision: the tensor core TRUNCATES the fp32 accumulator on every MMA (measured: relative
 // error ~2.7e-8 per accumulation, growing linearly with K; 1.4e-4 at K=16384), which is not FP32-class.
 // So accumulation is two-level: the dominant A_hi*B_hi term is summed in TMEM for only PCH K-chunks
 // (4*PCH MMAs) into one of two ping-pong accumulators, which four drain warps then add -- round-to-nearest,
 // on the CUDA cores -- into per-thread fp32 running sums while the MMA warp fills the other accumulator.
-// The two cross terms (2^-11 smaller) accumulate in a third TMEM region for the whole K loop.
+// The two cross terms (2^-11 smaller) accumulate in their own TMEM region for the whole tile (ping-pong per tile).
 //
-// Warp roles (320 threads):  0-3 drain + epilogue (TMEM lane quarter = warp id);  4-7 A producers;
-//                            8   TMEM allocator + TMA producer for B;             9   MMA issuer.
+// Persistent: grid = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...  Barrier phases run
+// continuously across tiles, the producers' prefetch runs across tile boundaries, and the drain warps run the
+// fused epilogue (scale/shift, residual, ReLU; coalesced through a small smem transpose) from registers while
+// the producers and the MMA warp are already working on the next tile.
+//
+// Warp roles (512 threads, register budgets re-balanced with setmaxnreg):
+//   WG0 warps 0-3   drain + epilogue (TMEM lane quarter = warp id)        200 regs
+//   WG1-2 warps 4-11 A producers                                          120 regs
+//   WG3 warp 12 TMEM allocator + TMA producer for B, warp 13 MMA issuer    40 regs
 #include <cuda.h>
 #include "conv_common.cuh"
 
@@ -27,7 +33,8 @@ namespace {
 
 constexpr int BM = 128, BK = 32, STAGES = 3;
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 512;
+constexpr int PF = 3;                       // producer prefetch ring depth (chunks of loads in flight per thread)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,9 +109,13 @@ struct Cfg {
   static constexpr int STG_OFFSET = BAR_OFFSET + 128;
   static constexpr int STG_BYTES = 4 * STG_ROWS * STG_LD * 4;   // 4 drain warps
   static constexpr int SMEM_BYTES = STG_OFFSET + STG_BYTES + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;      // cross-term accumulator + two ping-pong accumulators
+  static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
   // kind::tf32, D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+struct RowState {       // 4 output rows of one producer thread: image index and top-left input coordinate
+  int n[4], iy[4], ix[4];
 };
 
 template <int BN, bool SPLIT, int PCH>
@@ -117,26 +128,31 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   const uint32_t bar_base = smem_base + C::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };       // accumulator b ready to drain
-  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };   // accumulator b drained
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 4));
+  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };        // ping-pong accumulator b ready to drain
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };    // accumulator b drained
+  auto smallf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };  // cross-term accumulator b drained
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_k = p.K / BK;
+  const int num_g = (num_k + PCH - 1) / PCH;          // drain groups per tile
+  const int tiles_n = (p.Cout + BN - 1) / BN;
+  const int num_tiles = ((p.M + BM - 1) / BM) * tiles_n;
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 5);     // 4 producer warps + 1 arrive.expect_tx from the TMA lane
+      mbar_init(full_bar(s), 9);     // 8 producer warps + 1 arrive.expect_tx from the TMA lane
       mbar_init(empty_bar(s), 1);    // tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);     // tcgen05.commit
       mbar_init(acce_bar(b), 4);     // one lane per drain warp
+      mbar_init(smallf_bar(b), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -144,70 +160,75 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t tmem_small = tmem_d;                 // cross terms A_lo*B_hi + A_hi*B_lo
-  const int num_g = (num_k + PCH - 1) / PCH;          // drain groups
+  // TMEM columns: [0,BN) cross terms 0, [BN,2BN) cross terms 1, [2BN,3BN) main 0, [3BN,4BN) main 1
 
-  if (warp >= 4 && warp < 8) {
-    // =============================== A producers ===============================
-    const int t = threadIdx.x - 128;      // 0..127
+  if (warp >= 4 && warp < 12) {
+    // =============================== A producers (256 threads) ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    const int t = threadIdx.x - 128;      // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
-    const int rb = t >> 3;                // rows rb + 16*i
+    const int rb = t >> 3;                // rows rb + 32*i, i < 4
     const uint32_t sw_off = (uint32_t)((j ^ (rb & 7)) << 4);
-    int rn[8], riy[8], rix[8];
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && t == 0;
+    long long t_wait = 0, t_start = prof ? clock64() : 0;
+    const int total = my_tiles * num_k;
+
+    auto enter_tile = [&](int ti, RowState &rs) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int m0 = (tile / tiles_n) * BM;
+      const int hw = p.Ho * p.Wo;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rb + 16 * i;
-      if (m < p.M) {
-        const int hw = p.Ho * p.Wo;
-        const int n = m / hw;
-        const int r = m - n * hw;
-        const int oy = r / p.Wo, ox = r - oy * p.Wo;
-        rn[i] = n; riy[i] = oy * p.stride - p.pad_t; rix[i] = ox * p.stride - p.pad_l;
-      } else {
-        rn[i] = -1; riy[i] = 0; rix[i] = 0;
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + rb + 32 * i;
+        if (m < p.M) {
+          const int n = m / hw;
+          const int r = m - n * hw;
+          const int oy = r / p.Wo, ox = r - oy * p.Wo;
+          rs.n[i] = n; rs.iy[i] = oy * p.stride - p.pad_t; rs.ix[i] = ox * p.stride - p.pad_l;
+        } else {
+          rs.n[i] = -1; rs.iy[i] = 0; rs.ix[i] = 0;
+        }
       }
-    }
-    float4 cur[8], nxt[8];
-    uint32_t vmask_cur = 0, vmask_nxt = 0;
-    auto gather = [&](int kc, float4 *dst, uint32_t &vmask) {
-      const int kb = kc * BK;
+    };
+    RowState pf_rs, st_rs;                 // prefetch-side and store-side row state (may be one tile apart)
+    float4 ring[PF][4];
+    uint32_t vmask[PF];
+    int pf_kc = 0, pf_ti = 0;              // next chunk to prefetch
+    auto prefetch = [&](float4 *dst, uint32_t &vm) {
+      if (pf_kc == 0) enter_tile(pf_ti, pf_rs);
+      const int kb = pf_kc * BK;
       const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * 4;
       const int ky = tap / p.KW, kx = tap - ky * p.KW;
-      vmask = 0;
+      vm = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int iy = riy[i] + ky, ix = rix[i] + kx;
-        const bool ok = rn[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      for (int i = 0; i < 4; ++i) {
+        const int iy = pf_rs.iy[i] + ky, ix = pf_rs.ix[i] + kx;
+        const bool ok = pf_rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
         if (ok) {
-          dst[i] = __ldg(reinterpret_cast<const float4 *>(p.in + ((size_t)((size_t)rn[i] * p.H + iy) * p.W + ix) * p.in_ld + ci));
-          vmask |= 1u << i;
+          dst[i] = __ldg(reinterpret_cast<const float4 *>(p.in + ((size_t)((size_t)pf_rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci));
+          vm |= 1u << i;
         } else {
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (++pf_kc == num_k) { pf_kc = 0; ++pf_ti; }
     };
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0;
-    long long t_wait = 0, t_start = prof ? clock64() : 0;
-    if (num_k > 0) gather(0, cur, vmask_cur);
-    for (int kc = 0; kc < num_k; ++kc) {
-      const int s = kc % STAGES;
-      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      if (kc + 1 < num_k) gather(kc + 1, nxt, vmask_nxt);       // keep the next chunk's loads in flight
-      // prologue: per-channel affine (+ReLU) on real pixels only
-      if (p.pre_scale) {
-        const int kb = kc * BK;
-        const int ci = kb % p.Cin + j * 4;
+    int st_kc = 0, st_ti = 0;
+    auto consume = [&](int q, float4 *cur, uint32_t vm) {
+      if (st_kc == 0) enter_tile(st_ti, st_rs);
+      if (p.pre_scale) {                   // prologue: per-channel affine (+ReLU) on real pixels only
+        const int ci = (st_kc * BK) % p.Cin + j * 4;
         float4 sc, sh;
         if (p.pre_img_stride == 0) {
           sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + ci));
           sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + ci));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!(vmask_cur & (1u << i))) continue;
+        for (int i = 0; i < 4; ++i) {
+          if (!(vm & (1u << i))) continue;
           if (p.pre_img_stride != 0) {
-            sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + (size_t)rn[i] * p.pre_img_stride + ci));
-            sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + (size_t)rn[i] * p.pre_img_stride + ci));
+            sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + (size_t)st_rs.n[i] * p.pre_img_stride + ci));
+            sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + (size_t)st_rs.n[i] * p.pre_img_stride + ci));
           }
           float4 v = cur[i];
           v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
@@ -215,212 +236,255 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           cur[i] = v;
         }
       }
+      float4 hi[4], lo[4];                 // round-to-nearest TF32 head (zero-mean error), exact remainder rounded to TF32
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = cur[i];
+        hi[i].x = rn_tf32(v.x); hi[i].y = rn_tf32(v.y); hi[i].z = rn_tf32(v.z); hi[i].w = rn_tf32(v.w);
+        if (SPLIT) lo[i] = make_float4(rn_tf32(v.x - hi[i].x), rn_tf32(v.y - hi[i].y), rn_tf32(v.z - hi[i].z), rn_tf32(v.w - hi[i].w));
+      }
+      const int s = q % STAGES;
+      const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
       long long tw0 = prof ? clock64() : 0;
       mbar_wait(empty_bar(s), ph ^ 1u);
       if (prof) t_wait += clock64() - tw0;
       uint8_t *a_hi = smem + s * C::STAGE_BYTES;
       uint8_t *a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t off = (uint32_t)(rb + 16 * i) * 128u + sw_off;
-        const float4 v = cur[i];
-        float4 hi;      // round-to-nearest TF32 head (zero-mean error), exact remainder, remainder rounded to TF32
-        hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
-        *reinterpret_cast<float4 *>(a_hi + off) = hi;
-        if (SPLIT)
-          *reinterpret_cast<float4 *>(a_lo + off) =
-              make_float4(rn_tf32(v.x - hi.x), rn_tf32(v.y - hi.y), rn_tf32(v.z - hi.z), rn_tf32(v.w - hi.w));
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
+        *reinterpret_cast<float4 *>(a_hi + off) = hi[i];
+        if (SPLIT) *reinterpret_cast<float4 *>(a_lo + off) = lo[i];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(s));
+      if (++st_kc == num_k) { st_kc = 0; ++st_ti; }
+    };
+    // prime the ring with PF-1 chunks, then: issue chunk q+PF-1, consume chunk q
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-      vmask_cur = vmask_nxt;
+    for (int u = 0; u < PF - 1; ++u)
+      if (u < total) prefetch(ring[u], vmask[u]);
+    for (int q0 = 0; q0 < total; q0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int q = q0 + u;
+        if (q < total) {
+          if (q + PF - 1 < total) prefetch(ring[(u + PF - 1) % PF], vmask[(u + PF - 1) % PF]);
+          consume(q, ring[u], vmask[u]);
+        }
+      }
     }
     if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
-
   } else if (warp < 4) {
     // =============================== drain + epilogue ===============================
-    float sums[BN];
-#pragma unroll
-    for (int i = 0; i < BN; ++i) sums[i] = 0.f;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    long long t_wait = 0, t_start = prof ? clock64() : 0;
-    for (int g = 0; g < num_g; ++g) {
-      const int b = g & 1;
-      long long tw0 = prof ? clock64() : 0;
-      mbar_wait(accf_bar(b), (uint32_t)(g >> 1) & 1u);
-      if (prof) t_wait += clock64() - tw0;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * (1 + b) + c0), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(b));
-    }
-    if (SPLIT) {      // the last accf commit also covers every cross-term MMA
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_small + lane_off + (uint32_t)c0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);
-      }
-    }
-    long long t_epi0 = 0;
-    if (prof) { t_epi0 = clock64(); p.dbg[2] = t_epi0 - t_start; p.dbg[3] = t_wait; }
-    // Epilogue.  Each lane owns one accumulator ROW (TMEM lane), but global memory wants a warp to touch one
-    // row's contiguous columns at a time: transpose through a small padded smem tile, 8 rows per pass, then
-    // every warp-level access below is BN*4 contiguous bytes (residual load, output store).
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
     float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::STG_ROWS * C::STG_LD);
     constexpr int CPL = BN / 32;                 // consecutive columns per lane in the coalesced phase (4 or 2)
     const int col = lane * CPL;
-    const int co = n0 + col;
-    const bool cvalid = co < p.Cout;             // Cout % CPL == 0 is guaranteed by vec_out; ragged Cout takes the scalar path
-    float psc[CPL], psh[CPL];
-#pragma unroll
-    for (int e = 0; e < CPL; ++e) {
-      psc[e] = (p.post_scale && co + e < p.Cout) ? __ldg(p.post_scale + co + e) : 1.0f;
-      psh[e] = (p.post_shift && co + e < p.Cout) ? __ldg(p.post_shift + co + e) : 0.0f;
-    }
     const int hw = p.Ho * p.Wo;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      float sums[BN];
 #pragma unroll
-    for (int pass = 0; pass < 32 / C::STG_ROWS; ++pass) {
-      __syncwarp();
-      if ((lane / C::STG_ROWS) == pass) {        // the 8 lanes whose rows are staged in this pass
-        float *dst = stg + (lane % C::STG_ROWS) * C::STG_LD;
+      for (int i = 0; i < BN; ++i) sums[i] = 0.f;
+      for (int g = 0; g < num_g; ++g) {
+        const int G = ti * num_g + g;
+        const int b = G & 1;
+        long long tw0 = prof ? clock64() : 0;
+        mbar_wait(accf_bar(b), (uint32_t)(G >> 1) & 1u);
+        if (prof) t_wait += clock64() - tw0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(sums[c], sums[c + 1], sums[c + 2], sums[c + 3]);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * (2 + b) + c0), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar(b));
       }
-      __syncwarp();
-      // residual rows of this pass first (8 independent coalesced loads in flight), then the math and the stores
-      float rres[C::STG_ROWS][CPL];
-      if (p.res && p.vec_out && cvalid) {
+      if (SPLIT) {      // the tile's last accf commit also covers every cross-term MMA of the tile
+        const int sb = ti & 1;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * sb + c0), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smallf_bar(sb));
+      }
+      long long te0 = prof ? clock64() : 0;
+      // Epilogue (overlaps the next tile's main loop).  Each lane owns one accumulator ROW (TMEM lane), but global
+      // memory wants a warp to touch one row's contiguous columns at a time: transpose through a small padded smem
+      // tile, 8 rows per pass; every warp-level access below is BN*4 contiguous bytes (residual load, output store).
+      const int co = n0 + col;
+      const bool cvalid = co < p.Cout;
+      float psc[CPL], psh[CPL];
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) {
+        psc[e] = (p.post_scale && co + e < p.Cout) ? __ldg(p.post_scale + co + e) : 1.0f;
+        psh[e] = (p.post_shift && co + e < p.Cout) ? __ldg(p.post_shift + co + e) : 0.0f;
+      }
+#pragma unroll 1
+      for (int pass = 0; pass < 32 / C::STG_ROWS; ++pass) {
+        // residual rows of this pass first (8 independent coalesced loads in flight), then the math and the stores
+        float rres[C::STG_ROWS][CPL];
+        if (p.res && p.vec_out && cvalid) {
+#pragma unroll
+          for (int r = 0; r < C::STG_ROWS; ++r) {
+            const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) rres[r][e] = 0.f;
+            if (m < p.M) {
+              const int n = m / hw;
+              const int rr = m - n * hw;
+              const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+              const float *rp = p.res + (((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride) * p.res_ld + co;
+              if (CPL == 4) {
+                const float4 rv = __ldg(reinterpret_cast<const float4 *>(rp));
+                rres[r][0] = rv.x; rres[r][1] = rv.y; rres[r][CPL - 2] = rv.z; rres[r][CPL - 1] = rv.w;
+              } else {
+                const float2 rv = __ldg(reinterpret_cast<const float2 *>(rp));
+                rres[r][0] = rv.x; rres[r][1] = rv.y;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if ((lane / C::STG_ROWS) == pass) {        // the 8 lanes whose rows are staged in this pass
+          float *dst = stg + (lane % C::STG_ROWS) * C::STG_LD;
+#pragma unroll
+          for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(sums[c], sums[c + 1], sums[c + 2], sums[c + 3]);
+        }
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < C::STG_ROWS; ++r) {
           const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
+          if (m >= p.M) break;                     // warp-uniform
+          float x[CPL];
 #pragma unroll
-          for (int e = 0; e < CPL; ++e) rres[r][e] = 0.f;
-          if (m < p.M) {
-            const int n = m / hw;
-            const int rr = m - n * hw;
-            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-            const float *rp = p.res + (((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride) * p.res_ld + co;
-            if (CPL == 4) {
-              const float4 rv = __ldg(reinterpret_cast<const float4 *>(rp));
-              rres[r][0] = rv.x; rres[r][1] = rv.y; rres[r][CPL - 2] = rv.z; rres[r][CPL - 1] = rv.w;
-            } else {
-              const float2 rv = __ldg(reinterpret_cast<const float2 *>(rp));
-              rres[r][0] = rv.x; rres[r][1] = rv.y;
+          for (int e = 0; e < CPL; ++e) x[e] = stg[r * C::STG_LD + col + e] * psc[e] + psh[e];
+          if (!cvalid) continue;
+          if (p.vec_out) {
+            if (p.res) {
+#pragma unroll
+              for (int e = 0; e < CPL; ++e) x[e] += rres[r][e];
+            }
+            if (p.post_relu) {
+#pragma unroll
+              for (int e = 0; e < CPL; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
+            else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
+          } else {
+            size_t res_row = 0;
+            if (p.res) {
+              const int n = m / hw;
+              const int rr = m - n * hw;
+              const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+              res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+            }
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) {
+              if (co + e >= p.Cout) continue;
+              float y = x[e];
+              if (p.res) y += p.res[res_row * p.res_ld + co + e];
+              if (p.post_relu) y = fmaxf(y, 0.f);
+              p.out[(size_t)m * p.out_ld + co + e] = y;
             }
           }
         }
       }
-#pragma unroll
-      for (int r = 0; r < C::STG_ROWS; ++r) {
-        const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
-        if (m >= p.M) break;                     // warp-uniform
-        float x[CPL];
-#pragma unroll
-        for (int e = 0; e < CPL; ++e) x[e] = stg[r * C::STG_LD + col + e] * psc[e] + psh[e];
-        if (!cvalid) continue;
-        if (p.vec_out) {
-          if (p.res) {
-#pragma unroll
-            for (int e = 0; e < CPL; ++e) x[e] += rres[r][e];
-          }
-          if (p.post_relu) {
-#pragma unroll
-            for (int e = 0; e < CPL; ++e) x[e] = fmaxf(x[e], 0.f);
-          }
-          if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
-          else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
-        } else {
-          size_t res_row = 0;
-          if (p.res) {
-            const int n = m / hw;
-            const int rr = m - n * hw;
-            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-            res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
-          }
-#pragma unroll
-          for (int e = 0; e < CPL; ++e) {
-            if (co + e >= p.Cout) continue;
-            float y = x[e];
-            if (p.res) y += p.res[res_row * p.res_ld + co + e];
-            if (p.post_relu) y = fmaxf(y, 0.f);
-            p.out[(size_t)m * p.out_ld + co + e] = y;
-          }
-        }
-      }
+      if (prof) t_epi += clock64() - te0;
     }
-    if (prof) p.dbg[4] = clock64() - t_epi0;
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp == 8) {
-    // =============================== B producer (TMA) ===============================
-    if (lane == 0) {
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-      long long t_wait = 0, t_start = prof ? clock64() : 0;
-      for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-        long long tw0 = prof ? clock64() : 0;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        if (prof) t_wait += clock64() - tw0;
-        const uint32_t b_hi = smem_base + s * C::STAGE_BYTES + 2 * A_TILE_BYTES;
-        mbar_arrive_expect_tx(full_bar(s), SPLIT ? 2 * C::B_TILE_BYTES : C::B_TILE_BYTES);
-        tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BK, n0);
-        if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BK, n0);
-      }
-      if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
-    }
+    if (prof) { p.dbg[2] = clock64() - t_start; p.dbg[3] = t_wait; p.dbg[4] = t_epi; }
   } else {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-      long long t_wfull = 0, t_wacc = 0, t_start = prof ? clock64() : 0;
-      for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-        const int g = kc / PCH, b = g & 1;
-        const bool group_start = (kc % PCH) == 0;
-        long long tw0 = prof ? clock64() : 0;
-        if (group_start) mbar_wait(acce_bar(b), ((uint32_t)(g >> 1) & 1u) ^ 1u);    // accumulator b drained
-        long long tw1 = prof ? clock64() : 0;
-        mbar_wait(full_bar(s), ph);
-        if (prof) { t_wacc += tw1 - tw0; t_wfull += clock64() - tw1; }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_big = tmem_d + (uint32_t)(BN * (1 + b));
-        const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
-        const uint32_t a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-        const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
-        const uint64_t da_hi = make_smem_desc(a_hi), da_lo = make_smem_desc(a_lo);
-        const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_lo);
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {           // UMMA K = 8 for tf32 -> advance 32 bytes inside the swizzle atom
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          if (SPLIT) {
-            umma_tf32(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
-            umma_tf32(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 12) {
+      // =============================== B producer (TMA) ===============================
+      if (lane == 0) {
+        const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+        long long t_wait = 0, t_start = prof ? clock64() : 0;
+        int q = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+          const int n0 = (tile % tiles_n) * BN;
+          for (int kc = 0; kc < num_k; ++kc, ++q) {
+            const int s = q % STAGES;
+            const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+            long long tw0 = prof ? clock64() : 0;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            if (prof) t_wait += clock64() - tw0;
+            const uint32_t b_hi = smem_base + s * C::STAGE_BYTES + 2 * A_TILE_BYTES;
+            mbar_arrive_expect_tx(full_bar(s), SPLIT ? 2 * C::B_TILE_BYTES : C::B_TILE_BYTES);
+            tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BK, n0);
+            if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BK, n0);
           }
-          umma_tf32(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
         }
-        umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
-        if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
+        if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
       }
-      if (prof) { p.dbg[5] = clock64() - t_start; p.dbg[6] = t_wfull; p.dbg[7] = t_wacc; }
+    } else if (warp == 13) {
+      // =============================== MMA issuer ===============================
+      if (lane == 0) {
+        const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+        long long t_wfull = 0, t_wacc = 0, t_start = prof ? clock64() : 0;
+        int q = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          const int sb = ti & 1;
+          const uint32_t tmem_small = tmem_d + (uint32_t)(BN * sb);
+          if (SPLIT) {
+            long long tw0 = prof ? clock64() : 0;
+            mbar_wait(smallf_bar(sb), ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // cross-term accumulator of tile ti-2 drained
+            if (prof) t_wacc += clock64() - tw0;
+          }
+          for (int kc = 0; kc < num_k; ++kc, ++q) {
+            const int s = q % STAGES;
+            const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+            const int G = ti * num_g + kc / PCH, b = G & 1;
+            const bool group_start = (kc % PCH) == 0;
+            long long tw0 = prof ? clock64() : 0;
+            if (group_start) mbar_wait(acce_bar(b), ((uint32_t)(G >> 1) & 1u) ^ 1u);    // accumulator b drained
+            long long tw1 = prof ? clock64() : 0;
+            mbar_wait(full_bar(s), ph);
+            if (prof) { t_wacc += tw1 - tw0; t_wfull += clock64() - tw1; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_big = tmem_d + (uint32_t)(BN * (2 + b));
+            const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
+            const uint32_t a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+            const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+            const uint64_t da_hi = make_smem_desc(a_hi), da_lo = make_smem_desc(a_lo);
+            const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_lo);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {           // UMMA K = 8 for tf32 -> advance 32 bytes inside the swizzle atom
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              if (SPLIT) {
+                umma_tf32(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+                umma_tf32(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+              }
+              umma_tf32(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
+            }
+            umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
+            if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
+          }
+        }
+        if (prof) { p.dbg[5] = clock64() - t_start; p.dbg[6] = t_wfull; p.dbg[7] = t_wacc; }
+      }
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(C::TMEM_COLS));
   }
@@ -456,7 +520,15 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   alignas(64) CUtensorMap thi, tlo;
   memcpy(&thi, d->tmap_hi, sizeof(CUtensorMap));
   memcpy(&tlo, d->tmap_lo ? d->tmap_lo : d->tmap_hi, sizeof(CUtensorMap));
-  dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, BN));
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
+  dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
   conv_gemm_tc_kernel<BN, SPLIT, PCH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }

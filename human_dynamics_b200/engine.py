@@ -61,26 +61,58 @@ class HMMREngine(object):
         self._outs = {}
 
     # ---------------------------------------------------------------- stage API
-    def _resnet_plan(self, n, size):
-        key = (n, size)
+    EARLY_UNITS = 7          # bottleneck units of blocks 1-2 (3 + 4): stage A; blocks 3-4 are stage B
+
+    def _resnet_plan(self, n, size, stage='A'):
+        key = (n, size, stage)
         if key not in self._resnet_plans:
-            self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl)
+            nu = len(self.resnet.units)
+            cut = min(self.EARLY_UNITS, nu)
+            if stage == 'A':
+                self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(0, cut), root=True, tail=False)
+            else:
+                self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(cut, nu), root=False, tail=True)
         return self._resnet_plans[key]
 
+    def _trunk(self, images, phi, events=None):
+        """ResNet over N frames in two stages: root + blocks 1-2 per `frame_chunk` frames (working set near L2),
+        then blocks 3-4 + postnorm/mean per `late_chunk` frames (small maps need many frames to fill the SMs).
+        `events[i]` (optional) is waited on before chunk i of stage A (host->device copy of that chunk)."""
+        N, size = images.shape[0], images.shape[1]
+        st = current_stream()
+        cA = max(1, min(int(self.config.frame_chunk), N))
+        cB = max(1, min(int(self.config.late_chunk), N))
+        pa = self._resnet_plan(cA, size, 'A')
+        key = ('mid', N, size)
+        if key not in self._phi:
+            self._phi[key] = torch.empty((N, pa.out_hw, pa.out_hw, pa.out_depth), dtype=torch.float32, device=self.device)
+        mid = self._phi[key]
+        main = torch.cuda.current_stream()
+        for ci, i in enumerate(range(0, N, cA)):
+            n = min(cA, N - i)
+            plan = self._resnet_plan(n, size, 'A')
+            if events is not None:
+                main.wait_event(events[ci])
+            plan.set_output(mid[i:i + n])
+            plan.run(images[i:i + n], None, st)
+        for i in range(0, N, cB):
+            n = min(cB, N - i)
+            plan = self._resnet_plan(n, size, 'B')
+            plan.set_input(mid[i:i + n])
+            plan.run(None, phi[i:i + n], st)
+        return phi
+
     def encode_images(self, images, out=None):
-        """encoder_resnet: (N,H,W,3) float32 CUDA NHWC -> (N,2048).  Processes `frame_chunk` frames per pass."""
+        """encoder_resnet: (N,H,W,3) float32 CUDA NHWC -> (N,2048)."""
         if not images.is_cuda or images.dtype != torch.float32:
             raise _lib.HDError('encode_images: float32 CUDA tensor required (no CPU fallback exists)')
         if images.dim() != 4 or images.shape[3] != 3 or images.shape[1] != images.shape[2]:
             raise _lib.HDError('encode_images: expected (N,S,S,3) NHWC, got %s' % (tuple(images.shape),))
         images = images.contiguous()
-        N, size = images.shape[0], images.shape[1]
+        N = images.shape[0]
         phi = out if out is not None else torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=images.device)
-        chunk = max(1, min(int(self.config.frame_chunk), N)) if N else 1
-        st = current_stream()
-        for i in range(0, N, chunk):
-            n = min(chunk, N - i)
-            self._resnet_plan(n, size).run(images[i:i + n], phi[i:i + n], st)
+        if N:
+            self._trunk(images, phi)
         return phi
 
     def temporal_encode(self, feats):
@@ -192,11 +224,7 @@ class HMMREngine(object):
                 n = min(chunk, N - i)
                 dev_img[i:i + n].copy_(flat[i:i + n], non_blocking=True)
                 ev.record(cs)
-        st = current_stream()
-        for ev, i in zip(events, starts):
-            n = min(chunk, N - i)
-            main.wait_event(ev)
-            self._resnet_plan(n, S).run(dev_img[i:i + n], phi[i:i + n], st)
+        self._trunk(dev_img, phi, events)
         out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
         keys = [k for k in (fetch or self.FETCH_KEYS) if k in out]
         host, d2h = {}, 0
@@ -250,11 +278,3 @@ class HMMREngine(object):
         out['_movie_strips'] = strips
         return out
 
-    def num_launches(self, B, T, size=224, single_frame=False):
-        """Kernel launches of one predict() (for bench.py's gpu_launches claim; verified against hd_launch_count)."""
-        N = B * T
-        chunk = max(1, min(int(self.config.frame_chunk), N))
-        n = 0
-        for i in range(0, N, chunk):
-            n += self._resnet_plan(min(chunk, N - i), size).num_launches
-        return n

@@ -177,57 +177,107 @@ class PackedResNet(object):
 
 
 class ResNetPlan(object):
-    """Forward plan for a fixed number of frames n (activation buffers are reused across chunks)."""
+    """Forward plan for a fixed number of frames n (activation buffers are reused across chunks).
 
-    def __init__(self, packed: PackedResNet, n, size=224, impl='auto'):
+    `units=(lo, hi)` restricts the plan to bottleneck units [lo, hi) so the trunk can be run in two stages with
+    different frame counts: the early blocks have thousands of tiles per layer at any batch, the late blocks
+    (14x14 / 7x7 maps) only fill the 148 SMs when many frames are batched (wave quantisation).
+    root=True prepends conv1 + pool1; tail=True appends postnorm + global mean.
+    """
+
+    def __init__(self, packed: PackedResNet, n, size=224, impl='auto', units=None, root=True, tail=True):
         self.p = packed
         self.n = n
         self.size = size
+        self.root, self.tail = root, tail
         dev = packed.device
+        lo, hi = units if units is not None else (0, len(packed.units))
         H1 = size // 2                        # conv1 output (explicit pad 3, stride 2)
         H2 = (H1 + 1) // 2                    # pool1 SAME
-        big = n * H2 * H2 * 256               # also = n*H1*H1*64
-        self.bufA = torch.empty(big, dtype=torch.float32, device=dev)
-        self.bufB = torch.empty(big, dtype=torch.float32, device=dev)
-        self.bufS = torch.empty(max(big, n * H1 * H1 * 64), dtype=torch.float32, device=dev)
-        self.bufR1 = torch.empty(n * H2 * H2 * 64, dtype=torch.float32, device=dev)
-        self.bufR2 = torch.empty(n * H2 * H2 * 64, dtype=torch.float32, device=dev)
         self.H1, self.H2 = H1, H2
+        # spatial size / depth entering unit `lo`
+        H, d_in = H2, 64
+        for unit in packed.units[:lo]:
+            H = (H - 1) // unit['stride'] + 1
+            d_in = unit['depth']
+        self.in_hw, self.in_depth = H, d_in
+        # buffer sizes (floats per frame) needed by units [lo, hi)
+        mx_io, mx_r = H * H * d_in, 0
+        h = H
+        for unit in packed.units[lo:hi]:
+            ho = (h - 1) // unit['stride'] + 1
+            mx_io = max(mx_io, h * h * unit['depth'] if 'shortcut' in unit else 0, ho * ho * unit['depth'])
+            mx_r = max(mx_r, h * h * unit['base'])
+            h = ho
+        if root:
+            mx_io = max(mx_io, H1 * H1 * 64)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.bufA = torch.empty(n * mx_io, **f32)
+        self.bufB = torch.empty(n * mx_io, **f32)
+        self.bufS = torch.empty(n * mx_io, **f32)
+        self.bufR1 = torch.empty(max(1, n * mx_r), **f32)
+        self.bufR2 = torch.empty(max(1, n * mx_r), **f32)
         self.ops = []
+        self.in_refs = []                     # (op, 'in_' | 'res') descriptor fields that read the stage input
         x, y = self.bufA, self.bufB
-        H = H2
-        for unit in packed.units:
+        for ui, unit in enumerate(packed.units[lo:hi]):
             s = unit['stride']
             Ho = (H - 1) // s + 1
             pre = (unit['pre'][0], unit['pre'][1], 0, 1)
             if 'shortcut' in unit:
                 self.ops.append(unit['shortcut'].bind(x, n, H, H, self.bufS, pre=pre, impl=impl))
+                if ui == 0:
+                    self.in_refs.append((self.ops[-1], 'in_'))
                 res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
             else:
                 res, res_geom = x, (unit['depth'], H, H, s)      # identity, or max_pool2d(1x1, stride) = subsample
             self.ops.append(unit['conv1'].bind(x, n, H, H, self.bufR1, pre=pre, impl=impl))
+            if ui == 0:
+                self.in_refs.append((self.ops[-1], 'in_'))
             self.ops.append(unit['conv2'].bind(self.bufR1, n, H, H, self.bufR2, impl=impl))
             self.ops.append(unit['conv3'].bind(self.bufR2, n, Ho, Ho, y, res=res, res_geom=res_geom, impl=impl))
+            if ui == 0 and 'shortcut' not in unit:
+                self.in_refs.append((self.ops[-1], 'res'))
             x, y = y, x
             H = Ho
+            d_in = unit['depth']
         self.final = x
         self.final_hw = H * H
+        self.out_hw, self.out_depth = H, d_in
+        self.in_buf = self.bufA               # stage input when root=False
 
-    def run(self, images, out_phi, stream=None):
-        """images: (n,size,size,3) contiguous float32 CUDA view; out_phi: (n,2048) contiguous view."""
+    def set_input(self, t):
+        """Point the stage at an external input feature map [n, in_hw, in_hw, in_depth] (no copy)."""
+        for op, field in self.in_refs:
+            setattr(op.d, field, t.data_ptr())
+            op.keep = op.keep + (t,)
+
+    def set_output(self, t):
+        """Let the last unit write its output feature map [n, out_hw, out_hw, out_depth] straight into `t`."""
+        op = self.ops[-1]
+        op.d.out = t.data_ptr()
+        op.keep = op.keep + (t,)
+        self.final = t
+
+    def run(self, images, out, stream=None):
+        """root=True: images (n,size,size,3) contiguous float32 CUDA view; else `images` is ignored and the stage
+        input must already be in `in_buf` ([n, in_hw, in_hw, in_depth]).  tail=True: out = phi (n,2048) view;
+        else the stage output feature map is left in `self.final`."""
         st = current_stream() if stream is None else stream
         n, p = self.n, self.p
-        check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
-              'hd_conv1_7x7s2')
-        check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64, st), 'hd_maxpool3x3s2_same')
+        if self.root:
+            check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
+                  'hd_conv1_7x7s2')
+            check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64, st), 'hd_maxpool3x3s2_same')
         for op in self.ops:
             op.run(st)
-        check(lib.hd_bnrelu_avgpool(fptr(self.final), fptr(p.post[0]), fptr(p.post[1]), fptr(out_phi), n, self.final_hw,
-                                    p.out_dim, st), 'hd_bnrelu_avgpool')
+        if self.tail:
+            check(lib.hd_bnrelu_avgpool(fptr(self.final), fptr(p.post[0]), fptr(p.post[1]), fptr(out), n, self.final_hw,
+                                        p.out_dim, st), 'hd_bnrelu_avgpool')
 
     @property
     def num_launches(self):
-        return 3 + len(self.ops)
+        return (2 if self.root else 0) + len(self.ops) + (1 if self.tail else 0)
 
 
 # ------------------------------------------------------------------------------------------------
