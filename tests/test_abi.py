@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hd_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'hd_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(hd_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_symbols_exported_and_bound():
+    from human_dynamics_b200 import _lib
+    names = _declared()
+    assert len(names) >= 15
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), 'libhd_b200.so does not export %s' % n
+        assert n in _lib.SIGNATURES, 'ctypes binding missing for %s' % n
+    assert sorted(_lib.SIGNATURES) == names, 'binding table and header disagree'
+    assert _lib.lib.hd_version() >= 100
+    assert _lib.lib.hd_status_string(0) == b'ok' and _lib.lib.hd_status_string(4).startswith(b'unsupported')
+
+
+def test_struct_layouts_match_header_sizes():
+    """hd_conv_desc / hd_smpl_consts mirrors: field counts and natural-alignment sizes."""
+    from human_dynamics_b200 import _lib
+    assert ctypes.sizeof(_lib.ConvDesc) == 216
+    assert ctypes.sizeof(_lib.SmplConsts) == 16 + 9 * 8 + 24 * 4
+    assert _lib.ConvDesc.in_ld.offset == 8 and _lib.ConvDesc.w_kn.offset == 64 and _lib.ConvDesc.out.offset == 176
+
+
+def test_no_cpu_fallback_paths():
+    """Product code must not import the oracle, and ops must refuse CPU tensors."""
+    import torch
+    import pytest
+    for sub in ('human_dynamics_b200', 'src'):
+        for dp, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith('.py'):
+                    txt = open(os.path.join(dp, f)).read()
+                    assert not re.search(r'^\s*(from|import)\s+oracle', txt, flags=re.M), '%s imports the oracle' % f
+    from src.tf_smpl.batch_lbs import batch_rodrigues
+    from src.tf_smpl.projection import batch_orth_proj_idrot
+    from human_dynamics_b200._lib import HDError
+    with pytest.raises(HDError):
+        batch_rodrigues(torch.zeros(4, 3))
+    with pytest.raises(HDError):
+        batch_orth_proj_idrot(torch.zeros(2, 5, 3), torch.zeros(2, 3))
+    if not torch.cuda.is_available():
+        from human_dynamics_b200.engine import HMMREngine
+        with pytest.raises(HDError):
+            HMMREngine({}, {})
+
+
+def test_invalid_arguments_return_status_not_crash():
+    from human_dynamics_b200 import _lib
+    d = _lib.ConvDesc()
+    assert _lib.lib.hd_conv_gemm(ctypes.byref(d), None) == 1           # HD_ERR_INVALID: null in/out
+    assert b'null' in _lib.lib.hd_last_error()
+    assert _lib.lib.hd_rodrigues(None, None, 4, None) == 1
+    assert _lib.lib.hd_smpl_workspace_bytes(10) >= 10 * 24 * 21 * 4
