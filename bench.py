@@ -143,8 +143,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='hmmr', choices=['hmmr', 'single_frame', 'smpl'])
     ap.add_argument('--clips', type=int, default=32, help='clips per GPU (hmmr) / frames per GPU x 1 (single_frame: 64)')
-    ap.add_argument('--mode', default=os.environ.get('HD_IMPL', 'tc3'), choices=['tc3', 'simt', 'tc1'],
-                    help='tc3 = tcgen05 3xTF32 (FP32-class parity mode, the headline); tc1 = single-pass TF32 (fails parity)')
+    ap.add_argument('--mode', default=os.environ.get('HD_IMPL', 'auto'), choices=['auto', 'tc3h', 'tc3', 'simt', 'tc1'],
+                    help='auto/tc3h = tcgen05 fp16 head+remainder split x3 (FP32-class parity mode, the headline); tc3 = 3xTF32 (also FP32-class); '
+                         'tc1 = single-pass TF32 (fails parity); simt = exact FP32 CUDA cores')
     ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '64')))
     ap.add_argument('--late-chunk', type=int, default=int(os.environ.get('HD_LATE_CHUNK', '640')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -283,7 +284,8 @@ def main():
     if rank == 0:
         line = {'metric': metric, 'value': value, 'unit': unit_name, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32 (tcgen05 3xTF32 split, fp32 accumulate)' if args.mode == 'tc3' else ('f32' if args.mode == 'simt' else 'tf32'),
+                'dtype': {'auto': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)', 'tc3h': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)',
+                          'tc3': 'f32 (tcgen05 3xTF32 split, fp32 two-level accumulate)', 'simt': 'f32', 'tc1': 'tf32'}[args.mode],
                 'data': 'synthetic',
                 'config': {'workload': workload_name(args), 'mode': args.mode, 'frame_chunk': args.frame_chunk, 'late_chunk': args.late_chunk,
                            'l2': 'inputs larger than L2 (%.0f MB of frames per step vs 126 MB)' % (units_per_step * 224 * 224 * 3 * 4 / 1e6)
@@ -352,7 +354,7 @@ def measure_roofline(args, peaks, env):
             conv_time += t * reps
             if d.impl != _lib.HD_IMPL_SIMT or args.mode == 'simt':
                 tc_time += t * reps; tc_flops += fl * reps; n_tc += reps
-    kind = 'conv_gemm_tc_kernel (tcgen05 3xTF32 implicit GEMM, persistent)' if args.mode != 'simt' else 'conv_gemm_simt_kernel'
+    kind = 'conv_gemm_tc_kernel (tcgen05 implicit GEMM, %s, persistent)' % args.mode if args.mode != 'simt' else 'conv_gemm_simt_kernel'
     ach = tc_flops / tc_time / 1e12
     peak = peaks['bf16_tflops_sustained']
     step_s = env['ms'] * 1e-3
@@ -361,8 +363,8 @@ def measure_roofline(args, peaks, env):
             'share_of_step': tc_time / step_s,
             'note': 'algorithmic FLOPs (2*M*N*K, dense, as the reference computes them) of the %d conv launches of one step / their '
                     'CUDA-event durations (instrumented extra pass: one chunk of each trunk stage, scaled by its repeat count); '
-                    'peak = bf16 dense sustained (%s). The parity mode issues 3 TF32 MMAs per product and TF32 runs at half the '
-                    'bf16 rate, so its ceiling is 1/6 of this peak (%.0f TFLOP/s).' % (n_tc, peaks['source'], peak / 6)}
+                    'peak = bf16/fp16 dense sustained (%s). The parity modes issue 3 MMAs per product: ceiling = peak/3 (%.0f TFLOP/s) for the '
+                    'fp16 split, peak/6 for 3xTF32.' % (n_tc, peaks['source'], peak / 3)}
 
 
 if __name__ == '__main__':

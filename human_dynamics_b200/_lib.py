@@ -11,8 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhd_b200.so')
 
-HD_IMPL_SIMT, HD_IMPL_TC_3XTF32, HD_IMPL_TC_1XTF32 = 0, 1, 2
-IMPL_BY_NAME = {'simt': HD_IMPL_SIMT, 'tc3': HD_IMPL_TC_3XTF32, 'tc1': HD_IMPL_TC_1XTF32}
+HD_IMPL_SIMT, HD_IMPL_TC_3XTF32, HD_IMPL_TC_1XTF32, HD_IMPL_TC_3XF16 = 0, 1, 2, 3
+IMPL_BY_NAME = {'simt': HD_IMPL_SIMT, 'tc3': HD_IMPL_TC_3XTF32, 'tc1': HD_IMPL_TC_1XTF32, 'tc3h': HD_IMPL_TC_3XF16}
 
 
 class ConvDesc(C.Structure):
@@ -54,7 +54,7 @@ SIGNATURES = {
     'hd_launch_count_reset': (None, []),
     'hd_conv_gemm': (_i, [C.POINTER(ConvDesc), _vp]),
     'hd_conv_gemm_profile': (_i, [C.POINTER(ConvDesc), _vp, _vp]),
-    'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _vp]),
+    'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -23,18 +23,18 @@
 //
 // Warp roles (512 threads, register budgets re-balanced with setmaxnreg):
 //   WG0 warps 0-3   drain + epilogue (TMEM lane quarter = warp id)        200 regs
-//   WG1-2 warps 4-11 A producers                                          120 regs
+//   WG1-2 warps 4-11 A producers                                          136 regs
 //   WG3 warp 12 TMEM allocator + TMA producer for B, warp 13 MMA issuer    40 regs
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "conv_common.cuh"
 
 namespace hd {
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
-constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
+constexpr int BM = 128, STAGES = 3;
+constexpr int A_TILE_BYTES = BM * 128;      // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 fp16 of K)
 constexpr int NUM_THREADS = 512;
-constexpr int PF = 3;                       // producer prefetch ring depth (chunks of loads in flight per thread)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,6 +69,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -99,9 +105,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-template <int BN>
+template <int BN, bool HALF>
 struct Cfg {
-  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int BKE = HALF ? 64 : 32;                    // K elements per chunk (one 128-byte row)
+  static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STG_LD = BN + 4;                          // padded row of the epilogue staging tile (floats)
@@ -110,18 +117,22 @@ struct Cfg {
   static constexpr int STG_BYTES = 4 * STG_ROWS * STG_LD * 4;   // 4 drain warps
   static constexpr int SMEM_BYTES = STG_OFFSET + STG_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
-  // kind::tf32, D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2, N>>3 [17,23), M>>4 [24,29)
-  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10), b_format[10,13) (2 = TF32, 0 = F16), N>>3 [17,23), M>>4 [24,29)
+  static constexpr uint32_t FMT = HALF ? 0u : 2u;
+  static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static constexpr int PF = HALF ? 2 : 3;                       // producer prefetch ring depth (chunks in flight per thread)
+  static constexpr int V = HALF ? 2 : 1;                        // float4 loads per row per chunk per thread
 };
 
 struct RowState {       // 4 output rows of one producer thread: image index and top-left input coordinate
   int n[4], iy[4], ix[4];
 };
 
-template <int BN, bool SPLIT, int PCH>
+template <int BN, bool SPLIT, int PCH, bool HALF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, HALF>;
+  constexpr int BKE = C::BKE, PF = C::PF, V = C::V;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -134,7 +145,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = p.K / BK;
+  const int num_k = p.K / BKE;
   const int num_g = (num_k + PCH - 1) / PCH;          // drain groups per tile
   const int tiles_n = (p.Cout + BN - 1) / BN;
   const int num_tiles = ((p.M + BM - 1) / BM) * tiles_n;
@@ -160,11 +171,12 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  const int xmode = p.dbg ? (int)p.dbg[15] : 0;      // timing experiments (hd_conv_gemm_profile only; results invalid)
   // TMEM columns: [0,BN) cross terms 0, [BN,2BN) cross terms 1, [2BN,3BN) main 0, [3BN,4BN) main 1
 
   if (warp >= 4 && warp < 12) {
     // =============================== A producers (256 threads) ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int t = threadIdx.x - 128;      // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
     const int rb = t >> 3;                // rows rb + 32*i, i < 4
@@ -191,24 +203,27 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     };
     RowState pf_rs, st_rs;                 // prefetch-side and store-side row state (may be one tile apart)
-    float4 ring[PF][4];
+    float4 ring[PF][4 * V];
     uint32_t vmask[PF];
     int pf_kc = 0, pf_ti = 0;              // next chunk to prefetch
     auto prefetch = [&](float4 *dst, uint32_t &vm) {
       if (pf_kc == 0) enter_tile(pf_ti, pf_rs);
-      const int kb = pf_kc * BK;
-      const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * 4;
+      const int kb = pf_kc * BKE;
+      const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * (4 * V);
       const int ky = tap / p.KW, kx = tap - ky * p.KW;
       vm = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int iy = pf_rs.iy[i] + ky, ix = pf_rs.ix[i] + kx;
         const bool ok = pf_rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        if (ok) {
-          dst[i] = __ldg(reinterpret_cast<const float4 *>(p.in + ((size_t)((size_t)pf_rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci));
+        if (ok && !(xmode & 4)) {
+          const float4 *src = reinterpret_cast<const float4 *>(p.in + ((size_t)((size_t)pf_rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci);
+#pragma unroll
+          for (int v = 0; v < V; ++v) dst[i * V + v] = __ldg(src + v);
           vm |= 1u << i;
         } else {
-          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int v = 0; v < V; ++v) dst[i * V + v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (++pf_kc == num_k) { pf_kc = 0; ++pf_ti; }
@@ -216,33 +231,6 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     int st_kc = 0, st_ti = 0;
     auto consume = [&](int q, float4 *cur, uint32_t vm) {
       if (st_kc == 0) enter_tile(st_ti, st_rs);
-      if (p.pre_scale) {                   // prologue: per-channel affine (+ReLU) on real pixels only
-        const int ci = (st_kc * BK) % p.Cin + j * 4;
-        float4 sc, sh;
-        if (p.pre_img_stride == 0) {
-          sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + ci));
-          sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + ci));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!(vm & (1u << i))) continue;
-          if (p.pre_img_stride != 0) {
-            sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + (size_t)st_rs.n[i] * p.pre_img_stride + ci));
-            sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + (size_t)st_rs.n[i] * p.pre_img_stride + ci));
-          }
-          float4 v = cur[i];
-          v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
-          if (p.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          cur[i] = v;
-        }
-      }
-      float4 hi[4], lo[4];                 // round-to-nearest TF32 head (zero-mean error), exact remainder rounded to TF32
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = cur[i];
-        hi[i].x = rn_tf32(v.x); hi[i].y = rn_tf32(v.y); hi[i].z = rn_tf32(v.z); hi[i].w = rn_tf32(v.w);
-        if (SPLIT) lo[i] = make_float4(rn_tf32(v.x - hi[i].x), rn_tf32(v.y - hi[i].y), rn_tf32(v.z - hi[i].z), rn_tf32(v.w - hi[i].w));
-      }
       const int s = q % STAGES;
       const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
       long long tw0 = prof ? clock64() : 0;
@@ -250,11 +238,54 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       if (prof) t_wait += clock64() - tw0;
       uint8_t *a_hi = smem + s * C::STAGE_BYTES;
       uint8_t *a_lo = a_hi + A_TILE_BYTES;
+      const int pci = p.pre_scale ? (st_kc * BKE) % p.Cin + j * (4 * V) : 0;
+      // row by row (keeps the live set small): prologue affine (+ReLU) on real pixels only, then split every value into a
+      // head and a remainder that the tensor core reads exactly (zero-mean rounding):
+      //   TF32: hi = RN_tf32(x), lo = RN_tf32(x - hi);   FP16: hi = RN_f16(x), lo = RN_f16((x - hi) * 2^11)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        float xs[4 * V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float4 x = cur[i * V + v];
+          xs[4 * v] = x.x; xs[4 * v + 1] = x.y; xs[4 * v + 2] = x.z; xs[4 * v + 3] = x.w;
+        }
+        if (p.pre_scale && (vm & (1u << i))) {
+          const size_t po = (size_t)(p.pre_img_stride != 0 ? st_rs.n[i] : 0) * p.pre_img_stride + pci;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.pre_scale + po) + v);
+            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.pre_shift + po) + v);
+            xs[4 * v] = xs[4 * v] * sc.x + sh.x; xs[4 * v + 1] = xs[4 * v + 1] * sc.y + sh.y;
+            xs[4 * v + 2] = xs[4 * v + 2] * sc.z + sh.z; xs[4 * v + 3] = xs[4 * v + 3] * sc.w + sh.w;
+          }
+          if (p.pre_relu) {
+#pragma unroll
+            for (int e = 0; e < 4 * V; ++e) xs[e] = fmaxf(xs[e], 0.f);
+          }
+        }
+        uint32_t h[4], l[4];
+        if (!HALF) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float hf = rn_tf32(xs[e]);
+            h[e] = __float_as_uint(hf);
+            l[e] = __float_as_uint(rn_tf32(xs[e] - hf));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 hh = __floats2half2_rn(xs[2 * e], xs[2 * e + 1]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn((xs[2 * e] - hf.x) * 2048.0f, (xs[2 * e + 1] - hf.y) * 2048.0f);
+            h[e] = *reinterpret_cast<const uint32_t *>(&hh);
+            l[e] = *reinterpret_cast<const uint32_t *>(&ll);
+          }
+        }
         const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
-        *reinterpret_cast<float4 *>(a_hi + off) = hi[i];
-        if (SPLIT) *reinterpret_cast<float4 *>(a_lo + off) = lo[i];
+        if (xmode & 1) continue;
+        *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (SPLIT) *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async proxy)
       __syncwarp();
@@ -317,7 +348,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           uint32_t v[32];
           tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * sb + c0), v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]) * (HALF ? (1.0f / 2048.0f) : 1.0f);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -426,9 +457,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             mbar_wait(empty_bar(s), ph ^ 1u);
             if (prof) t_wait += clock64() - tw0;
             const uint32_t b_hi = smem_base + s * C::STAGE_BYTES + 2 * A_TILE_BYTES;
+            if (xmode & 2) { mbar_arrive(full_bar(s)); continue; }
             mbar_arrive_expect_tx(full_bar(s), SPLIT ? 2 * C::B_TILE_BYTES : C::B_TILE_BYTES);
-            tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BK, n0);
-            if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BK, n0);
+            tma_load_2d(b_hi, &tmap_hi, full_bar(s), kc * BKE, n0);
+            if (SPLIT) tma_load_2d(b_hi + C::B_TILE_BYTES, &tmap_lo, full_bar(s), kc * BKE, n0);
           }
         }
         if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
@@ -466,13 +498,19 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             const uint64_t da_hi = make_smem_desc(a_hi), da_lo = make_smem_desc(a_lo);
             const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_lo);
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {           // UMMA K = 8 for tf32 -> advance 32 bytes inside the swizzle atom
+            for (int k = 0; k < 4; ++k) {                // UMMA K = 8 tf32 / 16 fp16 = 32 bytes: advance inside the swizzle atom
               const uint64_t adv = (uint64_t)((k * 32) >> 4);
-              if (SPLIT) {
-                umma_tf32(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
-                umma_tf32(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+              if (HALF) {
+                umma_f16(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+                umma_f16(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+                umma_f16(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
+              } else {
+                if (SPLIT) {
+                  umma_tf32(tmem_small, da_lo + adv, db_hi + adv, C::IDESC, (kc | k) != 0);
+                  umma_tf32(tmem_small, da_hi + adv, db_lo + adv, C::IDESC, 1u);
+                }
+                umma_tf32(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
               }
-              umma_tf32(tmem_big, da_hi + adv, db_hi + adv, C::IDESC, !(group_start && k == 0));
             }
             umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
             if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
@@ -508,12 +546,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT, int PCH>
+template <int BN, bool SPLIT, int PCH, bool HALF>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, HALF>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
     configured = true;
   }
@@ -529,47 +567,51 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   }
   const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
   dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
-  conv_gemm_tc_kernel<BN, SPLIT, PCH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }
 
 }  // namespace
 
 int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
-  if (!d->tmap_hi || (d->impl == HD_IMPL_TC_3XTF32 && !d->tmap_lo)) {
+  if (!d->tmap_hi || (d->impl != HD_IMPL_TC_1XTF32 && !d->tmap_lo)) {
     set_last_error_text("hd_conv_gemm(tc): missing tensor maps");
     return HD_ERR_INVALID;
   }
-  if (p.Cin % BK != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % BK != 0 ||
+  const bool half = d->impl == HD_IMPL_TC_3XF16;
+  const int bke = half ? 64 : 32;
+  if (p.Cin % bke != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % bke != 0 ||
       (p.pre_scale && (!aligned16(p.pre_scale) || !aligned16(p.pre_shift) || p.pre_img_stride % 4 != 0))) {
-    set_last_error_text("hd_conv_gemm(tc): needs Cin % 32 == 0 and 16-byte aligned input / prologue vectors");
+    set_last_error_text("hd_conv_gemm(tc): needs Cin % 32 (tf32) / % 64 (fp16) == 0 and 16-byte aligned input / prologue vectors");
     return HD_ERR_INVALID;
   }
-  const bool split = d->impl == HD_IMPL_TC_3XTF32;
-  // 3xTF32: drain every 4 chunks = 16 truncating accumulations (~4e-7 relative, below fp32 SIMT summation noise);
+  const bool split = d->impl != HD_IMPL_TC_1XTF32;
+  // split modes: drain every 2 chunks = 8 truncating accumulations (~2e-7 relative, below fp32 SIMT summation noise;
+  // the drain warps are idle most of the time, so the extra drains are free);
   // 1xTF32 is ~1e-3 anyway: drain rarely
-  if (p.Cout <= 64) return split ? launch_tc<64, true, 4>(p, d, st) : launch_tc<64, false, 8>(p, d, st);
-  return split ? launch_tc<128, true, 4>(p, d, st) : launch_tc<128, false, 8>(p, d, st);
+  if (half) return p.Cout <= 64 ? launch_tc<64, true, 2, true>(p, d, st) : launch_tc<128, true, 2, true>(p, d, st);
+  if (p.Cout <= 64) return split ? launch_tc<64, true, 2, false>(p, d, st) : launch_tc<64, false, 8, false>(p, d, st);
+  return split ? launch_tc<128, true, 2, false>(p, d, st) : launch_tc<128, false, 8, false>(p, d, st);
 }
 
 }  // namespace hd
 
-// K-major weight matrix [rows, k_pad] fp32 -> CUtensorMap with a {32 x box_rows} box, 128-byte swizzle.
-// box_rows must equal the kernel's N tile: 64 when Cout <= 64, else 128.
-extern "C" int hd_make_weight_tmap(const float *w_nk, int rows, int k_pad, int box_rows, void *tmap_out) {
-  HD_REQUIRE(w_nk && tmap_out && rows > 0 && k_pad > 0 && k_pad % 32 == 0 && (box_rows == 64 || box_rows == 128) &&
-                 rows % box_rows == 0 && hd::aligned16(w_nk),
+// K-major weight matrix [rows, k_pad] (fp32 for the tf32 path, fp16 for the fp16 path) -> CUtensorMap with a
+// {128 bytes x box_rows} box and 128-byte swizzle.  box_rows must equal the kernel's N tile: 64 when Cout <= 64, else 128.
+extern "C" int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int box_rows, int elem_bytes, void *tmap_out) {
+  HD_REQUIRE(w_nk && tmap_out && rows > 0 && k_pad > 0 && (elem_bytes == 4 || elem_bytes == 2) && k_pad % (128 / elem_bytes) == 0 &&
+                 (box_rows == 64 || box_rows == 128) && rows % box_rows == 0 && hd::aligned16(w_nk),
              "hd_make_weight_tmap: bad arguments");
   hd::EncodeTiledFn fn = hd::get_encode_fn();
   if (!fn) { hd::set_last_error_text("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return HD_ERR_UNSUPPORTED; }
   alignas(64) CUtensorMap tm;
   const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)k_pad * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)k_pad * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w_nk), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(&tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_nk),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[96];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

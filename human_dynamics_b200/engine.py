@@ -42,7 +42,7 @@ class HMMREngine(object):
         self.config = config or HMMRConfig()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.impl = impl or self.config.impl
-        tc = self.impl in ('auto', 'tc3', 'tc1')
+        tc = self.impl if self.impl != 'simt' else False      # which tensor-core packing the layers carry
         w = load_weights(weights)
         self.delta_t_values = [int(d) for d in self.config.delta_t_values]
         with torch.cuda.device(self.device):

@@ -48,6 +48,16 @@ def tf32_split(w):
     return hi, lo
 
 
+def f16_split(w):
+    """w (float32) -> (hi, lo) float16: hi = RN_f16(w), lo = RN_f16((w - hi) * 2^11).  Same 11+11 significant bits as the
+    TF32 split at twice the tensor-core rate; the 2^11 scale keeps the remainder of small weights out of the fp16
+    subnormal range (the kernel accumulates the scaled cross terms separately and rescales once)."""
+    w = np.ascontiguousarray(w, np.float32)
+    hi = w.astype(np.float16)
+    lo = ((w - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+    return hi, lo
+
+
 class PackedConv(object):
     """Device-resident weights (+ epilogue vectors) of one conv / FC layer."""
 
@@ -66,24 +76,34 @@ class PackedConv(object):
         self.post_scale = _dev(post_scale, device) if post_scale is not None else None
         self.post_shift = _dev(post_shift, device) if post_shift is not None else None
         self.post_relu = bool(post_relu)
-        self.tc = False
+        self.tc = False            # False | 'f16' | 'tf32': which tensor-core packing this layer carries
         self.K_pad = 0
-        if tc and self.Cin % 32 == 0:
+        want = {True: 'f16', 'auto': 'f16', 'tc3h': 'f16', 'tc3': 'tf32', 'tc1': 'tf32'}.get(tc, tc)
+        if want == 'f16' and self.Cin % 64 != 0:
+            want = 'tf32'
+        if want in ('f16', 'tf32') and self.Cin % 32 == 0:
             self.K_pad = self.K
             box = 64 if self.Cout <= 64 else 128              # must equal the kernel's N tile (conv_tc.cu)
             rows = (self.Cout + box - 1) // box * box
             w_nk = np.zeros((rows, self.K_pad), np.float32)
             w_nk[:self.Cout] = w_kn.T
-            hi, lo = tf32_split(w_nk)
-            self.w_nk_hi = _dev(hi, device)
-            self.w_nk_lo = _dev(lo, device)
+            if want == 'f16':
+                hi, lo = f16_split(w_nk)
+                self.w_nk_hi = torch.from_numpy(hi).to(device)
+                self.w_nk_lo = torch.from_numpy(lo).to(device)
+                eb = 2
+            else:
+                hi, lo = tf32_split(w_nk)
+                self.w_nk_hi = _dev(hi, device)
+                self.w_nk_lo = _dev(lo, device)
+                eb = 4
             self.tmap_hi = (C.c_ubyte * 128)()
             self.tmap_lo = (C.c_ubyte * 128)()
-            check(lib.hd_make_weight_tmap(fptr(self.w_nk_hi), rows, self.K_pad, box, C.cast(self.tmap_hi, C.c_void_p)),
+            check(lib.hd_make_weight_tmap(C.c_void_p(self.w_nk_hi.data_ptr()), rows, self.K_pad, box, eb, C.cast(self.tmap_hi, C.c_void_p)),
                   'hd_make_weight_tmap')
-            check(lib.hd_make_weight_tmap(fptr(self.w_nk_lo), rows, self.K_pad, box, C.cast(self.tmap_lo, C.c_void_p)),
+            check(lib.hd_make_weight_tmap(C.c_void_p(self.w_nk_lo.data_ptr()), rows, self.K_pad, box, eb, C.cast(self.tmap_lo, C.c_void_p)),
                   'hd_make_weight_tmap')
-            self.tc = True
+            self.tc = want
 
     def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto'):
         """Fill a descriptor.  inp/out/res: CUDA float32 tensors (only their data_ptr is used).
@@ -114,11 +134,13 @@ class PackedConv(object):
                 res_geom = (self.Cout, Ho, Wo, 1)
             d.res_ld, d.res_H, d.res_W, d.res_stride = res_geom
         d.out = out.data_ptr(); d.out_ld = self.Cout if out_ld is None else out_ld
-        use_tc = self.tc and impl in ('auto', 'tc3', 'tc1') and (d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)
-        if impl in ('tc3', 'tc1') and not use_tc:
-            use_tc = False           # ragged layers always run on the exact-FP32 SIMT kernel
+        # ragged layers (Cin % 32 != 0, unaligned views) always run on the exact-FP32 SIMT kernel
+        use_tc = bool(self.tc) and impl in ('auto', 'tc3', 'tc1', 'tc3h') and (d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)
         if use_tc:
-            d.impl = _lib.HD_IMPL_TC_1XTF32 if impl == 'tc1' else _lib.HD_IMPL_TC_3XTF32
+            if self.tc == 'f16':
+                d.impl = _lib.HD_IMPL_TC_3XF16
+            else:
+                d.impl = _lib.HD_IMPL_TC_1XTF32 if impl == 'tc1' else _lib.HD_IMPL_TC_3XTF32
             d.w_nk_hi, d.w_nk_lo = self.w_nk_hi.data_ptr(), self.w_nk_lo.data_ptr()
             d.tmap_hi = C.cast(self.tmap_hi, C.c_void_p)
             d.tmap_lo = C.cast(self.tmap_lo, C.c_void_p)

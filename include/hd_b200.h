@@ -53,15 +53,16 @@ void hd_launch_count_reset(void);
  *   if post_relu: v = max(v,0)
  *   out[(n*Ho+oy)*Wo+ox][co] = v
  * ------------------------------------------------------------------------------------------ */
-enum { HD_IMPL_SIMT = 0, HD_IMPL_TC_3XTF32 = 1, HD_IMPL_TC_1XTF32 = 2 };
+enum { HD_IMPL_SIMT = 0, HD_IMPL_TC_3XTF32 = 1, HD_IMPL_TC_1XTF32 = 2, HD_IMPL_TC_3XF16 = 3 };
 
 typedef struct {
   const float *in;  long long in_ld;          /* floats between consecutive pixels (>= Cin) */
   int n_img, H, W, Cin;
   int Ho, Wo, KH, KW, stride, pad_t, pad_l;
   const float *w_kn;                          /* [K, Cout] row-major, K=(ky,kx,ci) (TF HWIO flattened) */
-  const float *w_nk_hi;                       /* [Cout_pad, K_pad] K-major, tf32-truncated (tensor-core path) */
-  const float *w_nk_lo;                       /* residual w - w_hi, same layout (3xTF32 only) */
+  const void *w_nk_hi;                        /* [Cout_pad, K] K-major head of the split weights: fp32 holding TF32 values (impl 1,2)
+                                                 or fp16 (impl 3) */
+  const void *w_nk_lo;                        /* remainder, same layout: RN_tf32(w - hi), or RN_f16((w - hi) * 2^11) */
   int Cout;  int K_pad;
   const float *pre_scale, *pre_shift;  int pre_img_stride;  int pre_relu;
   const float *post_scale, *post_shift;  int post_relu;
@@ -76,9 +77,10 @@ int hd_conv_gemm(const hd_conv_desc *d, void *stream);
  * (device int64; layout in conv_simt.cu).  Tuning aid, not part of the reference surface. */
 int hd_conv_gemm_profile(const hd_conv_desc *d, void *stream, long long *dbg);
 
-/* Encode the TMA descriptor (CUtensorMap, 128 B, written to host memory `tmap_out`) for a K-major
- * weight matrix [rows, k_pad] fp32 with a {32 x box_rows} box and 128-byte swizzle. */
-int hd_make_weight_tmap(const float *w_nk, int rows, int k_pad, int box_rows, void *tmap_out);
+/* Encode the TMA descriptor (CUtensorMap, 128 B, written to host memory `tmap_out`) for a K-major weight matrix
+ * [rows, k_pad] of elem_bytes-wide elements (4 = fp32/tf32 path, 2 = fp16 path) with a {128 bytes x box_rows} box and
+ * 128-byte swizzle. */
+int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int box_rows, int elem_bytes, void *tmap_out);
 
 /* ---- ResNet root / tail pieces (slim resnet_v2_50, called from src/models.py:65-74) ---- */
 /* conv1: 7x7 stride 2, explicit zero pad 3+3, + bias.  in [N,H,W,3] -> out [N,H/2,W/2,64]; w [7*7*3,64]. */

@@ -15,7 +15,7 @@ class FeatureExtractor(object):
         self.batch_size = batch_size
         w = load_weights(model_path)
         self.device = torch.device('cuda', torch.cuda.current_device())
-        self.packed = PackedResNet(w, self.device, tc=impl in ('auto', 'tc3', 'tc1'))
+        self.packed = PackedResNet(w, self.device, tc=(impl if impl != 'simt' else False))
         self.plan = ResNetPlan(self.packed, batch_size, img_size, impl)
         self.phis = torch.empty((batch_size, self.packed.out_dim), dtype=torch.float32, device=self.device)
 

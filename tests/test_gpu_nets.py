@@ -22,7 +22,7 @@ def _conv_case(rng, n, H, W, Cin, Cout, KH, KW, stride, pad, pre=None, res=None,
     ps = rng.uniform(0.5, 1.5, size=Cout).astype(np.float32) if post_scale else None
     pb = rng.normal(0, 0.2, size=Cout).astype(np.float32)
     dev = torch.device('cuda')
-    pc = PackedConv(w, dev, ps, pb, relu, stride=stride, pad=pad, tc=(impl != 'simt'))
+    pc = PackedConv(w, dev, ps, pb, relu, stride=stride, pad=pad, tc=(impl if impl != 'simt' else False))
     xt = torch.from_numpy(x).to(dev)
     pre_t = None
     a = torch.from_numpy(x).double()
@@ -98,13 +98,27 @@ def test_conv_gemm_tcgen05_3xtf32(case):
     assert err < 5e-5, err        # tensor-core fp32 accumulation truncates: grows slowly with K (K=6144 -> ~3e-5)
 
 
+F16_CASES = [c for c in TC_CASES if c[3] % 64 == 0]
+
+
+@pytest.mark.parametrize('case', F16_CASES)
+def test_conv_gemm_tcgen05_3xf16(case):
+    """fp16 head/remainder split (11+11 significant bits, remainder scaled by 2^11): same accuracy class as 3xTF32."""
+    from human_dynamics_b200 import _lib
+    rng = np.random.RandomState(hash(case) % (2 ** 31))
+    err, op = _conv_case(rng, *case, impl='tc3h')
+    assert op.d.impl == _lib.HD_IMPL_TC_3XF16, 'fp16 tensor-core path was not selected'
+    print('tc3h rel err %.3e (K=%d)' % (err, case[3] * case[5] * case[6]))
+    assert err < 5e-5, err
+
+
 def test_conv_gemm_tcgen05_1xtf32_is_tf32_accurate():
     rng = np.random.RandomState(3)
     err, _ = _conv_case(rng, 4, 28, 28, 128, 128, 3, 3, 1, (1, 1), None, None, True, True, impl='tc1')
     assert 1e-5 < err < 5e-3, err          # single-pass TF32: ~1e-3, NOT the parity mode
 
 
-@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('impl', ['simt', 'tc3', 'auto'])
 @pytest.mark.parametrize('n,size', [(3, 64), (2, 224)])
 def test_resnet_matches_oracle(weights, impl, n, size):
     from human_dynamics_b200 import synthetic
@@ -112,7 +126,7 @@ def test_resnet_matches_oracle(weights, impl, n, size):
     from oracle import nets_ref
     img = synthetic.make_images(n, seed=n, size=size)
     dev = torch.device('cuda')
-    plan = ResNetPlan(PackedResNet(weights, dev, tc=(impl != 'simt')), n, size, impl)
+    plan = ResNetPlan(PackedResNet(weights, dev, tc=(impl if impl != 'simt' else False)), n, size, impl)
     phi = torch.empty((n, 2048), dtype=torch.float32, device=dev)
     plan.run(torch.from_numpy(img).to(dev), phi)
     torch.cuda.synchronize()
@@ -129,7 +143,7 @@ def test_fmovie_matches_oracle(weights, impl):
     B, T = 3, 20
     x = np.random.RandomState(0).normal(0, 1, size=(B, T, 2048)).astype(np.float32)
     dev = torch.device('cuda')
-    plan = FMoviePlan(PackedFMovie(weights, dev, 3, tc=(impl != 'simt')), B, T, impl)
+    plan = FMoviePlan(PackedFMovie(weights, dev, 3, tc=(impl if impl != 'simt' else False)), B, T, impl)
     y = plan.run(torch.from_numpy(x).to(dev))
     torch.cuda.synchronize()
     ref = nets_ref.az_fc2_groupnorm(x, weights, 3).numpy()
@@ -143,7 +157,7 @@ def test_ief_matches_oracle(weights, impl):
     N = 45
     phi = np.random.RandomState(1).normal(0, 1, size=(N, 2048)).astype(np.float32)
     dev = torch.device('cuda')
-    packed = PackedIEF(weights, dev, tc=(impl != 'simt'))
+    packed = PackedIEF(weights, dev, tc=(impl if impl != 'simt' else False))
     plan = IEFPlan(packed, N, impl=impl)
     theta0 = packed.mean_param.expand(N, 85).contiguous()
     theta, deltas = plan.run(torch.from_numpy(phi).to(dev), theta0)
@@ -164,7 +178,7 @@ def _check_predict(got, ref, keys=None):
         assert rel_err(g, v) < REL, (k, rel_err(g, v))
 
 
-@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('impl', ['simt', 'tc3', 'auto'])
 def test_full_window_matches_oracle(weights, smpl_model, impl):
     """BASELINE config 3 wiring at B=2, T=20, 224x224 (oracle ResNet on 40 frames takes ~10 s)."""
     from human_dynamics_b200 import synthetic, HMMRConfig

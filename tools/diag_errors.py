@@ -17,7 +17,7 @@ def fc_err(K, impl, M=512, N=256, seed=0):
     rng = np.random.RandomState(seed)
     x = rng.normal(0, 1, size=(M, K)).astype(np.float32)
     w = (rng.normal(0, 1, size=(K, N)) / np.sqrt(K)).astype(np.float32)
-    pc = PackedConv(w, torch.device('cuda'), tc=(impl != 'simt'))
+    pc = PackedConv(w, torch.device('cuda'), tc=(impl if impl != 'simt' else False))
     out = torch.empty((M, N), device='cuda')
     pc.bind(torch.from_numpy(x).cuda(), M, 1, 1, out, impl=impl).run(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
@@ -26,7 +26,7 @@ def fc_err(K, impl, M=512, N=256, seed=0):
 
 
 for K in (64, 256, 1024, 2304, 4608, 6144, 16384):
-    print('K=%5d  simt %.2e  tc3 %.2e  tc1 %.2e' % (K, fc_err(K, 'simt'), fc_err(K, 'tc3'), fc_err(K, 'tc1')), flush=True)
+    print('K=%5d  simt %.2e  tc3 %.2e  tc3h %.2e  tc1 %.2e' % (K, fc_err(K, 'simt'), fc_err(K, 'tc3'), fc_err(K, 'tc3h'), fc_err(K, 'tc1')), flush=True)
 
 w = synthetic.make_synthetic_weights(seed=1)
 smpl = synthetic.make_synthetic_smpl(seed=2)
@@ -36,7 +36,7 @@ ref64 = nets_ref.hmmr_predict(img, w, smpl, dtype=torch.float64)
 ref32 = nets_ref.hmmr_predict(img, w, smpl)
 keys = ['_phi', '_movie_strips', 'omegas', 'verts', 'joints', 'kps', 'omegas_delta', 'verts_delta']
 print('oracle f32 vs f64: ' + '  '.join('%s %.1e' % (k, rel(ref32[k], ref64[k])) for k in keys))
-for impl in ('simt', 'tc3', 'tc1'):
+for impl in ('simt', 'tc3', 'tc3h'):
     eng = HMMREngine(w, smpl, HMMRConfig(batch_size=B, sequence_length=T, frame_chunk=16), impl=impl)
     got = eng.predict(torch.from_numpy(img).cuda())
     torch.cuda.synchronize()

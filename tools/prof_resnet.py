@@ -9,7 +9,7 @@ chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 mode = sys.argv[2] if len(sys.argv) > 2 else 'tc3'
 w = synthetic.make_resnet_weights(seed=1)
 dev = torch.device('cuda')
-plan = ResNetPlan(PackedResNet(w, dev, tc=(mode != 'simt')), chunk, 224, mode)
+plan = ResNetPlan(PackedResNet(w, dev, tc=(mode if mode != 'simt' else False)), chunk, 224, mode)
 x = torch.from_numpy(synthetic.make_images(chunk, seed=0)).to(dev)
 phi = torch.empty((chunk, 2048), device=dev)
 for _ in range(2):

@@ -10,7 +10,7 @@ NAMES = ['prod_loop', 'prod_wait_empty', 'drain_loop', 'drain_wait_accf', 'epilo
 dev = torch.device('cuda')
 rng = np.random.RandomState(0)
 cases = [  # n, H, Cin, Cout, k, stride, residual, pre
-    (32, 14, 256, 256, 3, 1, False, False),
+    (48, 14, 256, 256, 3, 1, False, False),
     (32, 28, 128, 128, 3, 1, False, False),
     (32, 56, 64, 256, 1, 1, True, False),
     (32, 56, 256, 64, 1, 1, False, True),
@@ -19,15 +19,25 @@ cases = [  # n, H, Cin, Cout, k, stride, residual, pre
 ]
 for n, H, Cin, Cout, k, s, res, pre in cases:
     w = (rng.normal(0, 1, size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
-    pc = PackedConv(w, dev, np.ones(Cout, np.float32), np.zeros(Cout, np.float32), True, stride=s, pad=(k // 2, k // 2), tc=True)
+    pc = PackedConv(w, dev, np.ones(Cout, np.float32), np.zeros(Cout, np.float32), True, stride=s, pad=(k // 2, k // 2), tc=os.environ.get('HD_IMPL', 'tc3h'))
     x = torch.randn((n, H, H, Cin), device=dev)
     out = torch.empty((n, H, H, Cout), device=dev)
     r = torch.randn((n, H, H, Cout), device=dev) if res else None
     pr = (torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev), 0, 1) if pre else None
-    op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl='tc3')
-    dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+    op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl=os.environ.get('HD_IMPL', 'tc3h'))
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for _ in range(3):
+    modes = [int(a) for a in sys.argv[1:]] or [0]
+    for mode in modes:
+        dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+        dbg[15] = mode
+        for _ in range(3):
+            check(lib.hd_conv_gemm_profile(op.ref, st, C.c_void_p(dbg.data_ptr())))
+        torch.cuda.synchronize()
+        if mode:
+            d = dbg.cpu().numpy()
+            print('   [xmode %d: 1=no A STS, 2=no B TMA, 4=no A loads]  ' % mode + '  '.join('%s=%d' % (nm, v) for nm, v in zip(NAMES, d)))
+    dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+    for _ in range(2):
         check(lib.hd_conv_gemm_profile(op.ref, st, C.c_void_p(dbg.data_ptr())))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
