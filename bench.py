@@ -54,7 +54,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -62,9 +62,12 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -74,7 +77,9 @@ class ClockSampler(object):
             pass
         sm, smax, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        time.sleep(0.15)
+        inside = [ln for ts, ln in self.lines if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.1)]
+        for ln in (inside if len(inside) >= 2 else [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 7:
                 continue
@@ -230,21 +235,23 @@ def main():
             return h2d, d2h
 
     # ------------------------------------------------------------------ device-resident timing (value)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                    # started before warm-up so nvidia-smi is already looping when the timed region begins
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     _lib.lib.hd_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_end = sampler.mark()
     launches = int(_lib.lib.hd_launch_count())
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:
         tms = torch.tensor([ms], device=dev)

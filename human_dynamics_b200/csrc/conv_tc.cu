@@ -115,7 +115,8 @@ struct Cfg {
   static constexpr int STG_ROWS = 8;                            // rows staged per warp per pass
   static constexpr int STG_OFFSET = BAR_OFFSET + 128;
   static constexpr int STG_BYTES = 4 * STG_ROWS * STG_LD * 4;   // 4 drain warps
-  static constexpr int SMEM_BYTES = STG_OFFSET + STG_BYTES + 1024;   // + alignment slack
+  static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
+  static constexpr int SMEM_BYTES = LUT_OFFSET + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
   // D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10), b_format[10,13) (2 = TF32, 0 = F16), N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t FMT = HALF ? 0u : 2u;
@@ -128,7 +129,7 @@ struct RowState {       // 4 output rows of one producer thread: image index and
   int n[4], iy[4], ix[4];
 };
 
-template <int BN, bool SPLIT, int PCH, bool HALF>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
   using C = Cfg<BN, HALF>;
@@ -145,7 +146,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = p.K / BKE;
+  const int num_k = (GATHER ? p.K_pad : p.K) / BKE;   // GATHER: ragged Cin (conv1: K=147 zero-padded to 192)
   const int num_g = (num_k + PCH - 1) / PCH;          // drain groups per tile
   const int tiles_n = (p.Cout + BN - 1) / BN;
   const int num_tiles = ((p.M + BM - 1) / BM) * tiles_n;
@@ -170,6 +171,19 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (GATHER) {      // k = (ky*KW + kx)*Cin + ci  ->  ky<<24 | kx<<16 | (kx*Cin + ci); 0xFFFFFFFF beyond K
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + C::LUT_OFFSET);
+    for (int k = threadIdx.x; k < 256; k += NUM_THREADS) {
+      uint32_t e = 0xFFFFFFFFu;
+      if (k < p.K) {
+        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        e = ((uint32_t)ky << 24) | ((uint32_t)kx << 16) | (uint32_t)(kx * p.Cin + ci);
+      }
+      lut[k] = e;
+    }
+    __syncthreads();
+  }
   const uint32_t tmem_d = *tmem_slot;
   const int xmode = p.dbg ? (int)p.dbg[15] : 0;      // timing experiments (hd_conv_gemm_profile only; results invalid)
   // TMEM columns: [0,BN) cross terms 0, [BN,2BN) cross terms 1, [2BN,3BN) main 0, [3BN,4BN) main 1
@@ -208,6 +222,30 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     int pf_kc = 0, pf_ti = 0;              // next chunk to prefetch
     auto prefetch = [&](float4 *dst, uint32_t &vm) {
       if (pf_kc == 0) enter_tile(pf_ti, pf_rs);
+      if (GATHER) {          // element-wise gather through the k -> (ky, kx, offset) table (L1-resident input rows)
+        const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + C::LUT_OFFSET) + pf_kc * BKE + j * (4 * V);
+        uint32_t ent[4 * V];
+#pragma unroll
+        for (int e = 0; e < 4 * V; ++e) ent[e] = lut[e];
+        vm = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float xs[4 * V];
+          const float *rowp = p.in + ((size_t)(pf_rs.n[i] < 0 ? 0 : pf_rs.n[i]) * p.H * p.W) * p.in_ld;
+#pragma unroll
+          for (int e = 0; e < 4 * V; ++e) {
+            const int ky = (int)(ent[e] >> 24), kx = (int)((ent[e] >> 16) & 0xFF), off = (int)(ent[e] & 0xFFFF);
+            const int iy = pf_rs.iy[i] + ky, ix = pf_rs.ix[i] + kx;
+            const bool ok = ent[e] != 0xFFFFFFFFu && pf_rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            xs[e] = ok ? __ldg(rowp + ((long long)iy * p.W + pf_rs.ix[i]) * p.in_ld + off) : 0.f;
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) dst[i * V + v] = make_float4(xs[4 * v], xs[4 * v + 1], xs[4 * v + 2], xs[4 * v + 3]);
+          if (pf_rs.n[i] >= 0) vm |= 1u << i;
+        }
+        if (++pf_kc == num_k) { pf_kc = 0; ++pf_ti; }
+        return;
+      }
       const int kb = pf_kc * BKE;
       const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * (4 * V);
       const int ky = tap / p.KW, kx = tap - ky * p.KW;
@@ -546,12 +584,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT, int PCH, bool HALF>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   using C = Cfg<BN, HALF>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
     configured = true;
   }
@@ -567,7 +605,7 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   }
   const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
   dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
-  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -580,6 +618,14 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
   }
   const bool half = d->impl == HD_IMPL_TC_3XF16;
   const int bke = half ? 64 : 32;
+  if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded
+    if (p.K_pad % 64 != 0 || p.K_pad < p.K || p.K_pad > 256 || p.Cout > 64 || p.pre_scale || p.KW > 255 || p.KH > 255 ||
+        p.KW * p.Cin > 65535) {
+      set_last_error_text("hd_conv_gemm(tc gather): needs K_pad % 64 == 0, K <= K_pad <= 256, Cout <= 64, no prologue");
+      return HD_ERR_INVALID;
+    }
+    return launch_tc<64, true, 2, true, true>(p, d, st);
+  }
   if (p.Cin % bke != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % bke != 0 ||
       (p.pre_scale && (!aligned16(p.pre_scale) || !aligned16(p.pre_shift) || p.pre_img_stride % 4 != 0))) {
     set_last_error_text("hd_conv_gemm(tc): needs Cin % 32 (tf32) / % 64 (fp16) == 0 and 16-byte aligned input / prologue vectors");

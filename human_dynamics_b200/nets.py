@@ -79,14 +79,16 @@ class PackedConv(object):
         self.tc = False            # False | 'f16' | 'tf32': which tensor-core packing this layer carries
         self.K_pad = 0
         want = {True: 'f16', 'auto': 'f16', 'tc3h': 'f16', 'tc3': 'tf32', 'tc1': 'tf32'}.get(tc, tc)
-        if want == 'f16' and self.Cin % 64 != 0:
+        gather = want == 'f16' and self.Cin % 32 != 0 and self.K <= 256 and self.Cout <= 64   # conv1: element-wise gather
+        if want == 'f16' and self.Cin % 64 != 0 and not gather:
             want = 'tf32'
-        if want in ('f16', 'tf32') and self.Cin % 32 == 0:
-            self.K_pad = self.K
+        self.gather = bool(gather)
+        if want in ('f16', 'tf32') and (self.Cin % 32 == 0 or gather):
+            self.K_pad = (self.K + 63) // 64 * 64 if gather else self.K
             box = 64 if self.Cout <= 64 else 128              # must equal the kernel's N tile (conv_tc.cu)
             rows = (self.Cout + box - 1) // box * box
             w_nk = np.zeros((rows, self.K_pad), np.float32)
-            w_nk[:self.Cout] = w_kn.T
+            w_nk[:self.Cout, :self.K] = w_kn.T
             if want == 'f16':
                 hi, lo = f16_split(w_nk)
                 self.w_nk_hi = torch.from_numpy(hi).to(device)
@@ -135,7 +137,8 @@ class PackedConv(object):
             d.res_ld, d.res_H, d.res_W, d.res_stride = res_geom
         d.out = out.data_ptr(); d.out_ld = self.Cout if out_ld is None else out_ld
         # ragged layers (Cin % 32 != 0, unaligned views) always run on the exact-FP32 SIMT kernel
-        use_tc = bool(self.tc) and impl in ('auto', 'tc3', 'tc1', 'tc3h') and (d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)
+        use_tc = bool(self.tc) and impl in ('auto', 'tc3', 'tc1', 'tc3h') and \
+            (self.gather or ((d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)))
         if use_tc:
             if self.tc == 'f16':
                 d.impl = _lib.HD_IMPL_TC_3XF16
@@ -172,6 +175,8 @@ class PackedResNet(object):
         self.blocks = blocks
         self.conv1_w = _dev(np.asarray(w[p + '/conv1/weights'], np.float32).reshape(147, 64), device)
         self.conv1_b = _dev(w[p + '/conv1/biases'], device)
+        # conv2d_same(7x7, stride 2): explicit pad 3+3 then VALID (A.2); tensor-core path gathers the ragged K=147 element-wise
+        self.conv1 = PackedConv(w[p + '/conv1/weights'], device, post_shift=w[p + '/conv1/biases'], stride=2, pad=(3, 3), tc=tc)
         self.units = []
         d_in = 64
         for b, (base, units, bstride) in enumerate(blocks, start=1):
@@ -240,6 +245,9 @@ class ResNetPlan(object):
         self.bufR1 = torch.empty(max(1, n * mx_r), **f32)
         self.bufR2 = torch.empty(max(1, n * mx_r), **f32)
         self.ops = []
+        self.conv1_op = None
+        if root and packed.conv1.tc and impl != 'simt':
+            self.conv1_op = packed.conv1.bind(self.bufS, n, size, size, self.bufS, in_ld=3, impl=impl)   # `in_` is set per run
         self.in_refs = []                     # (op, 'in_' | 'res') descriptor fields that read the stage input
         x, y = self.bufA, self.bufB
         for ui, unit in enumerate(packed.units[lo:hi]):
@@ -288,8 +296,12 @@ class ResNetPlan(object):
         st = current_stream() if stream is None else stream
         n, p = self.n, self.p
         if self.root:
-            check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
-                  'hd_conv1_7x7s2')
+            if self.conv1_op is not None:
+                self.conv1_op.d.in_ = images.data_ptr()
+                self.conv1_op.run(st)
+            else:
+                check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
+                      'hd_conv1_7x7s2')
             check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64, st), 'hd_maxpool3x3s2_same')
         for op in self.ops:
             op.run(st)

@@ -98,7 +98,10 @@ def test_conv_gemm_tcgen05_3xtf32(case):
     assert err < 5e-5, err        # tensor-core fp32 accumulation truncates: grows slowly with K (K=6144 -> ~3e-5)
 
 
-F16_CASES = [c for c in TC_CASES if c[3] % 64 == 0]
+F16_CASES = [c for c in TC_CASES if c[3] % 64 == 0] + [
+    (2, 12, 12, 3, 64, 7, 7, 2, (3, 3), None, None, False, False),      # conv1: ragged K=147 through the gather producer
+    (3, 224, 224, 3, 64, 7, 7, 2, (3, 3), None, None, False, False),
+]
 
 
 @pytest.mark.parametrize('case', F16_CASES)
