@@ -30,6 +30,9 @@ class ConvDesc(C.Structure):
         ('out', C.c_void_p), ('out_ld', C.c_longlong),
         ('impl', C.c_int),
         ('tmap_hi', C.c_void_p), ('tmap_lo', C.c_void_p),
+        ('in_hi', C.c_void_p), ('in_lo', C.c_void_p),
+        ('out_hi', C.c_void_p), ('out_lo', C.c_void_p), ('out2_ld', C.c_longlong),
+        ('post2_scale', C.c_void_p), ('post2_shift', C.c_void_p), ('post2_relu', C.c_int),
     ]
 
 
@@ -56,7 +59,7 @@ SIGNATURES = {
     'hd_conv_gemm_profile': (_i, [C.POINTER(ConvDesc), _vp, _vp]),
     'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_groupnorm_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'hd_ief_delta_init': (_i, [_vp, _vp, _i, _i, _vp]),

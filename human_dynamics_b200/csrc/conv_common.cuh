@@ -14,15 +14,21 @@ struct ConvParams {
   float *out; long long out_ld;
   int vec_out;   // out/res/post vectors allow float4 access
   int K_pad;     // tensor-core path: padded K of the packed weights
+  const void *in_hi, *in_lo;      // pre-split fp16 activations (cp.async producer) or nullptr
+  void *out_hi, *out_lo; long long out2_ld;
+  const float *post2_scale, *post2_shift; int post2_relu;
   long long *dbg;  // optional: per-role cycle counters of CTA (0,0) (hd_conv_gemm_profile), else nullptr
 };
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
-  if (!d || !d->in || !d->out) { set_last_error_text("hd_conv_gemm: null in/out"); return HD_ERR_INVALID; }
+  if (!d || !(d->in || (d->in_hi && d->in_lo)) || !(d->out || (d->out_hi && d->out_lo))) {
+    set_last_error_text("hd_conv_gemm: null in/out");
+    return HD_ERR_INVALID;
+  }
   if (d->n_img <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0 ||
-      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || d->in_ld < d->Cin || d->out_ld < d->Cout) {
+      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || d->in_ld < d->Cin || (d->out && d->out_ld < d->Cout) || (d->out_hi && d->out2_ld < d->Cout)) {
     set_last_error_text("hd_conv_gemm: bad shape");
     return HD_ERR_INVALID;
   }
@@ -45,7 +51,10 @@ inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
   p.post_scale = d->post_scale; p.post_shift = d->post_shift; p.post_relu = d->post_relu;
   p.res = d->res; p.res_ld = d->res_ld; p.res_H = d->res_H; p.res_W = d->res_W; p.res_stride = d->res_stride;
   p.out = d->out; p.out_ld = d->out_ld;
-  p.vec_out = (d->Cout % 4 == 0) && (d->out_ld % 4 == 0) && aligned16(d->out) &&
+  p.in_hi = d->in_hi; p.in_lo = d->in_lo; p.out_hi = d->out_hi; p.out_lo = d->out_lo; p.out2_ld = d->out2_ld;
+  p.post2_scale = d->post2_scale; p.post2_shift = d->post2_shift; p.post2_relu = d->post2_relu;
+  p.vec_out = (d->Cout % 4 == 0) && (!d->out || ((d->out_ld % 4 == 0) && aligned16(d->out))) &&
+              (!d->out_hi || ((d->out2_ld % 4 == 0) && aligned16(d->out_hi) && aligned16(d->out_lo))) &&
               (!d->res || ((d->res_ld % 4 == 0) && aligned16(d->res))) &&
               (!d->post_scale || aligned16(d->post_scale)) && (!d->post_shift || aligned16(d->post_shift));
   p.K_pad = d->K_pad;

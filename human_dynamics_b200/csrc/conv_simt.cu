@@ -217,7 +217,10 @@ int launch(const ConvParams &p, cudaStream_t st) {
 }  // namespace
 
 int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
-  if (!p.w_kn) { set_last_error_text("hd_conv_gemm(simt): w_kn is null"); return HD_ERR_INVALID; }
+  if (!p.w_kn || !p.in || !p.out || p.out_hi) {
+    set_last_error_text("hd_conv_gemm(simt): needs w_kn and fp32 in/out (no pre-split activations)");
+    return HD_ERR_INVALID;
+  }
   const bool fasta = (p.Cin % 8 == 0) && (p.in_ld % 4 == 0) && aligned16(p.in) &&
                      (!p.pre_scale || true);
   const bool vecb = (p.Cout % 4 == 0) && aligned16(p.w_kn);

@@ -91,6 +91,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Nearest value with the low 13 mantissa bits clear (all the tf32 datapath reads).
 __device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
@@ -129,7 +136,7 @@ struct RowState {       // 4 output rows of one producer thread: image index and
   int n[4], iy[4], ix[4];
 };
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
   using C = Cfg<BN, HALF>;
@@ -216,6 +223,49 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
     };
+    if (ASPLIT) {
+      // ---- pre-split fp16 activations: cp.async straight into the swizzled tile, STAGES chunks in flight, no registers ----
+      const __half *ihi = reinterpret_cast<const __half *>(p.in_hi);
+      const __half *ilo = reinterpret_cast<const __half *>(p.in_lo);
+      RowState rs;
+      int kc = 0, ti = 0;
+      constexpr int LAG = STAGES - 1;        // chunk q is signalled after chunk q+LAG has been issued
+      for (int q = 0; q < total; ++q) {
+        if (kc == 0) enter_tile(ti, rs);
+        const int s = q % STAGES;
+        const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+        long long tw0 = prof ? clock64() : 0;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (prof) t_wait += clock64() - tw0;
+        const int kb = kc * BKE;
+        const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * 8;
+        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        const uint32_t a_hi = smem_base + s * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int iy = rs.iy[i] + ky, ix = rs.ix[i] + kx;
+          const bool ok = rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const size_t e = ok ? ((size_t)((size_t)rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci : 0;
+          const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
+          cp_async16(a_hi + off, ihi + e, ok ? 16u : 0u);
+          cp_async16(a_lo + off, ilo + e, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (q >= LAG) {
+          cp_async_wait<LAG>();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar((q - LAG) % STAGES));
+        }
+        if (++kc == num_k) { kc = 0; ++ti; }
+      }
+      cp_async_wait<0>();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        for (int q = (total > LAG ? total - LAG : 0); q < total; ++q) mbar_arrive(full_bar(q % STAGES));
+      if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
+    } else {
     RowState pf_rs, st_rs;                 // prefetch-side and store-side row state (may be one tile apart)
     float4 ring[PF][4 * V];
     uint32_t vmask[PF];
@@ -345,6 +395,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     }
     if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
+    }   // !ASPLIT
   } else if (warp < 4) {
     // =============================== drain + epilogue ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
@@ -453,8 +504,34 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
               for (int e = 0; e < CPL; ++e) x[e] = fmaxf(x[e], 0.f);
             }
-            if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
-            else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
+            if (p.out) {
+              if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
+              else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
+            }
+            if (p.out_hi) {      // the next layer's A operand: second affine (+ReLU) = its pre-activation, pre-split into fp16 head/remainder
+              uint32_t hp[CPL / 2], lp[CPL / 2];
+#pragma unroll
+              for (int e = 0; e < CPL; e += 2) {
+                float y0 = x[e], y1 = x[e + 1];
+                if (p.post2_scale) { y0 *= __ldg(p.post2_scale + co + e); y1 *= __ldg(p.post2_scale + co + e + 1); }
+                if (p.post2_shift) { y0 += __ldg(p.post2_shift + co + e); y1 += __ldg(p.post2_shift + co + e + 1); }
+                if (p.post2_relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                const __half2 hh = __floats2half2_rn(y0, y1);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((y0 - hf.x) * 2048.0f, (y1 - hf.y) * 2048.0f);
+                hp[e / 2] = *reinterpret_cast<const uint32_t *>(&hh);
+                lp[e / 2] = *reinterpret_cast<const uint32_t *>(&ll);
+              }
+              __half *oh = reinterpret_cast<__half *>(p.out_hi) + (size_t)m * p.out2_ld + co;
+              __half *ol = reinterpret_cast<__half *>(p.out_lo) + (size_t)m * p.out2_ld + co;
+              if (CPL == 4) {
+                *reinterpret_cast<uint2 *>(oh) = make_uint2(hp[0], hp[CPL / 2 - 1]);
+                *reinterpret_cast<uint2 *>(ol) = make_uint2(lp[0], lp[CPL / 2 - 1]);
+              } else {
+                *reinterpret_cast<uint32_t *>(oh) = hp[0];
+                *reinterpret_cast<uint32_t *>(ol) = lp[0];
+              }
+            }
           } else {
             size_t res_row = 0;
             if (p.res) {
@@ -584,12 +661,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   using C = Cfg<BN, HALF>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
     configured = true;
   }
@@ -605,7 +682,7 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   }
   const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
   dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
-  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -618,6 +695,17 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
   }
   const bool half = d->impl == HD_IMPL_TC_3XF16;
   const int bke = half ? 64 : 32;
+  if ((p.out_hi || p.in_hi) && (!half || !p.vec_out)) {
+    set_last_error_text("hd_conv_gemm(tc): pre-split activations need impl 3 and 16-byte aligned, 4-column-multiple outputs");
+    return HD_ERR_INVALID;
+  }
+  if (p.in_hi) {                       // pre-split fp16 activations: cp.async producer
+    if (p.Cin % 64 != 0 || p.K % 64 != 0 || p.in_ld % 8 != 0 || !aligned16(p.in_hi) || !aligned16(p.in_lo) || p.pre_scale) {
+      set_last_error_text("hd_conv_gemm(tc split-A): needs Cin % 64 == 0, in_ld % 8 == 0, aligned in_hi/in_lo, no prologue");
+      return HD_ERR_INVALID;
+    }
+    return p.Cout <= 64 ? launch_tc<64, true, 2, true, false, true>(p, d, st) : launch_tc<128, true, 2, true, false, true>(p, d, st);
+  }
   if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded
     if (p.K_pad % 64 != 0 || p.K_pad < p.K || p.K_pad > 256 || p.Cout > 64 || p.pre_scale || p.KW > 255 || p.KH > 255 ||
         p.KW * p.Cin > 65535) {
@@ -626,7 +714,7 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
     }
     return launch_tc<64, true, 2, true, true>(p, d, st);
   }
-  if (p.Cin % bke != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % bke != 0 ||
+  if (!p.in || p.Cin % bke != 0 || p.in_ld % 4 != 0 || !aligned16(p.in) || p.K % bke != 0 ||
       (p.pre_scale && (!aligned16(p.pre_scale) || !aligned16(p.pre_shift) || p.pre_img_stride % 4 != 0))) {
     set_last_error_text("hd_conv_gemm(tc): needs Cin % 32 (tf32) / % 64 (fp16) == 0 and 16-byte aligned input / prologue vectors");
     return HD_ERR_INVALID;

@@ -1,11 +1,13 @@
 // Small non-GEMM pieces of the network path: ResNet root/tail, GroupNorm statistics, IEF glue.
+#include <cuda_fp16.h>
 #include "conv_common.cuh"
 
 namespace {
 
 // pool1 (slim.max_pool2d 3x3/2 'SAME'): padded cells are ignored.
 __global__ void maxpool3x3s2_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4,
-                                    int Ho, int Wo, int pt, int pl) {
+                                    int Ho, int Wo, int pt, int pl, const float4 *__restrict__ scale,
+                                    const float4 *__restrict__ shift, uint2 *__restrict__ out_hi, uint2 *__restrict__ out_lo) {
   const long long total = (long long)N * Ho * Wo * C4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -28,6 +30,22 @@ __global__ void maxpool3x3s2_kernel(const float4 *__restrict__ in, float4 *__res
     }
   }
   out[i] = m;
+  if (out_hi) {        // relu(bn(x)) of the first bottleneck unit, as an fp16 head/remainder pair
+    const float4 sc = __ldg(scale + c), sh = __ldg(shift + c);
+    const float y[4] = {fmaxf(m.x * sc.x + sh.x, 0.f), fmaxf(m.y * sc.y + sh.y, 0.f), fmaxf(m.z * sc.z + sh.z, 0.f),
+                        fmaxf(m.w * sc.w + sh.w, 0.f)};
+    uint32_t hp[2], lp[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const __half2 hh = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn((y[2 * e] - hf.x) * 2048.0f, (y[2 * e + 1] - hf.y) * 2048.0f);
+      hp[e] = *reinterpret_cast<const uint32_t *>(&hh);
+      lp[e] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    out_hi[i] = make_uint2(hp[0], hp[1]);
+    out_lo[i] = make_uint2(lp[0], lp[1]);
+  }
 }
 
 // postnorm BN + ReLU + mean over HW.  One thread per (n, c); consecutive threads -> consecutive channels.
@@ -102,14 +120,18 @@ int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *ou
   return hd::launch_conv_simt(p, (cudaStream_t)stream);
 }
 
-int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, void *stream) {
+int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, const float *scale, const float *shift,
+                         void *out_hi, void *out_lo, void *stream) {
   HD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hd_maxpool3x3s2_same: bad arguments");
+  HD_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && (!out_hi || (scale && shift)), "hd_maxpool3x3s2_same: split output needs scale, shift, out_hi and out_lo");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int pth = (Ho - 1) * 2 + 3 - H, ptw = (Wo - 1) * 2 + 3 - W;
   const int pt = (pth > 0 ? pth : 0) / 2, pl = (ptw > 0 ? ptw : 0) / 2;
   const long long total = (long long)N * Ho * Wo * (C / 4);
   maxpool3x3s2_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N, H, W, C / 4, Ho, Wo, pt, pl);
+      reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N, H, W, C / 4, Ho, Wo, pt, pl,
+      reinterpret_cast<const float4 *>(scale), reinterpret_cast<const float4 *>(shift), reinterpret_cast<uint2 *>(out_hi),
+      reinterpret_cast<uint2 *>(out_lo));
   return hd::check_launch("maxpool3x3s2_kernel");
 }
 

@@ -69,7 +69,9 @@ class HMMREngine(object):
             nu = len(self.resnet.units)
             cut = min(self.EARLY_UNITS, nu)
             if stage == 'A':
-                self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(0, cut), root=True, tail=False)
+                nxt = self.resnet.units[cut]['pre'] if cut < nu else None
+                self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(0, cut), root=True, tail=False,
+                                                     next_pre=nxt)
             else:
                 self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(cut, nu), root=False, tail=True)
         return self._resnet_plans[key]
@@ -87,18 +89,25 @@ class HMMREngine(object):
         if key not in self._phi:
             self._phi[key] = torch.empty((N, pa.out_hw, pa.out_hw, pa.out_depth), dtype=torch.float32, device=self.device)
         mid = self._phi[key]
+        mid_split = None
+        if pa.split and pa.out_split is not None:
+            skey = ('mid16', N, size)
+            if skey not in self._phi:
+                self._phi[skey] = (torch.empty(mid.shape, dtype=torch.float16, device=self.device),
+                                   torch.empty(mid.shape, dtype=torch.float16, device=self.device))
+            mid_split = self._phi[skey]
         main = torch.cuda.current_stream()
         for ci, i in enumerate(range(0, N, cA)):
             n = min(cA, N - i)
             plan = self._resnet_plan(n, size, 'A')
             if events is not None:
                 main.wait_event(events[ci])
-            plan.set_output(mid[i:i + n])
+            plan.set_output(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
             plan.run(images[i:i + n], None, st)
         for i in range(0, N, cB):
             n = min(cB, N - i)
             plan = self._resnet_plan(n, size, 'B')
-            plan.set_input(mid[i:i + n])
+            plan.set_input(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
             plan.run(None, phi[i:i + n], st)
         return phi
 

@@ -107,15 +107,21 @@ class PackedConv(object):
                   'hd_make_weight_tmap')
             self.tc = want
 
-    def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto'):
+    def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto',
+             inp_split=None, out_split=None, post2=None):
         """Fill a descriptor.  inp/out/res: CUDA float32 tensors (only their data_ptr is used).
 
         pre = (scale, shift, img_stride, relu); res_geom = (res_ld, res_H, res_W, res_stride).
+        inp_split = (hi, lo) fp16 tensors: pre-activated, pre-split A operand (then `inp` may be None);
+        out_split = (hi, lo) fp16 tensors + post2 = (scale|None, shift|None, relu): second output (then `out` may be None).
         """
         d = ConvDesc()
         Ho = (H + 2 * self.pad_t - self.KH) // self.stride + 1 if self.KH > 1 else (H - 1) // self.stride + 1
         Wo = (W + 2 * self.pad_l - self.KW) // self.stride + 1 if self.KW > 1 else (W - 1) // self.stride + 1
-        d.in_ = inp.data_ptr(); d.in_ld = self.Cin if in_ld is None else in_ld
+        d.in_ = inp.data_ptr() if inp is not None else None
+        d.in_ld = self.Cin if in_ld is None else in_ld
+        if inp_split is not None:
+            d.in_hi, d.in_lo = inp_split[0].data_ptr(), inp_split[1].data_ptr()
         d.n_img, d.H, d.W, d.Cin = n_img, H, W, self.Cin
         d.Ho, d.Wo, d.KH, d.KW = Ho, Wo, self.KH, self.KW
         d.stride, d.pad_t, d.pad_l = self.stride, self.pad_t, self.pad_l
@@ -135,10 +141,21 @@ class PackedConv(object):
             if res_geom is None:
                 res_geom = (self.Cout, Ho, Wo, 1)
             d.res_ld, d.res_H, d.res_W, d.res_stride = res_geom
-        d.out = out.data_ptr(); d.out_ld = self.Cout if out_ld is None else out_ld
+        d.out = out.data_ptr() if out is not None else None
+        d.out_ld = self.Cout if out_ld is None else out_ld
+        if out_split is not None:
+            d.out_hi, d.out_lo, d.out2_ld = out_split[0].data_ptr(), out_split[1].data_ptr(), self.Cout
+            if post2 is not None:
+                if post2[0] is not None:
+                    d.post2_scale = post2[0].data_ptr()
+                if post2[1] is not None:
+                    d.post2_shift = post2[1].data_ptr()
+                d.post2_relu = int(post2[2])
         # ragged layers (Cin % 32 != 0, unaligned views) always run on the exact-FP32 SIMT kernel
         use_tc = bool(self.tc) and impl in ('auto', 'tc3', 'tc1', 'tc3h') and \
-            (self.gather or ((d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)))
+            (self.gather or inp_split is not None or ((d.in_ld % 4 == 0) and (inp.data_ptr() % 16 == 0)))
+        if (inp_split is not None or out_split is not None) and not (use_tc and self.tc == 'f16'):
+            raise _lib.HDError('pre-split activations need the fp16 tensor-core packing (impl auto / tc3h, Cin % 64 == 0)')
         if use_tc:
             if self.tc == 'f16':
                 d.impl = _lib.HD_IMPL_TC_3XF16
@@ -149,7 +166,7 @@ class PackedConv(object):
             d.tmap_lo = C.cast(self.tmap_lo, C.c_void_p)
         else:
             d.impl = _lib.HD_IMPL_SIMT
-        return ConvOp(d, (self, inp, out, pre, res), (Ho, Wo))
+        return ConvOp(d, (self, inp, out, pre, res, inp_split, out_split, post2), (Ho, Wo))
 
 
 class ConvOp(object):
@@ -212,7 +229,7 @@ class ResNetPlan(object):
     root=True prepends conv1 + pool1; tail=True appends postnorm + global mean.
     """
 
-    def __init__(self, packed: PackedResNet, n, size=224, impl='auto', units=None, root=True, tail=True):
+    def __init__(self, packed: PackedResNet, n, size=224, impl='auto', units=None, root=True, tail=True, next_pre=None):
         self.p = packed
         self.n = n
         self.size = size
@@ -239,54 +256,107 @@ class ResNetPlan(object):
         if root:
             mx_io = max(mx_io, H1 * H1 * 64)
         f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        # split mode: every conv reads its A operand as a pre-activated fp16 head/remainder pair written by the producing
+        # epilogue (cp.async straight into the swizzled tile); fp32 copies exist only where a residual needs them
+        self.split = impl in ('auto', 'tc3h') and all(
+            c.tc == 'f16' and not c.gather for u in packed.units[lo:hi] for k, c in u.items() if isinstance(c, PackedConv))
         self.bufA = torch.empty(n * mx_io, **f32)
         self.bufB = torch.empty(n * mx_io, **f32)
         self.bufS = torch.empty(n * mx_io, **f32)
-        self.bufR1 = torch.empty(max(1, n * mx_r), **f32)
-        self.bufR2 = torch.empty(max(1, n * mx_r), **f32)
         self.ops = []
         self.conv1_op = None
         if root and packed.conv1.tc and impl != 'simt':
             self.conv1_op = packed.conv1.bind(self.bufS, n, size, size, self.bufS, in_ld=3, impl=impl)   # `in_` is set per run
-        self.in_refs = []                     # (op, 'in_' | 'res') descriptor fields that read the stage input
+        self.in_refs = []                     # (op, field) descriptor fields that read the stage input
+        self.pool_split = None
         x, y = self.bufA, self.bufB
-        for ui, unit in enumerate(packed.units[lo:hi]):
-            s = unit['stride']
-            Ho = (H - 1) // s + 1
-            pre = (unit['pre'][0], unit['pre'][1], 0, 1)
-            if 'shortcut' in unit:
-                self.ops.append(unit['shortcut'].bind(x, n, H, H, self.bufS, pre=pre, impl=impl))
+        units = packed.units[lo:hi]
+        if self.split:
+            def pair(count):
+                return (torch.empty(max(1, count), **f16), torch.empty(max(1, count), **f16))
+            xs, ys = pair(n * mx_io), pair(n * mx_io)
+            r1, r2 = pair(n * mx_r), pair(n * mx_r)
+            self.in_split = xs
+            if root:
+                self.pool_split = (units[0]['pre'][0], units[0]['pre'][1], xs)
+            self.out_split = None
+            for ui, unit in enumerate(units):
+                s = unit['stride']
+                Ho = (H - 1) // s + 1
+                if 'shortcut' in unit:
+                    self.ops.append(unit['shortcut'].bind(None, n, H, H, self.bufS, inp_split=xs, impl=impl))
+                    if ui == 0:
+                        self.in_refs += [(self.ops[-1], 'in_hi', 0), (self.ops[-1], 'in_lo', 1)]
+                    res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
+                else:
+                    res, res_geom = x, (unit['depth'], H, H, s)
+                self.ops.append(unit['conv1'].bind(None, n, H, H, None, inp_split=xs, out_split=r1, impl=impl))
                 if ui == 0:
-                    self.in_refs.append((self.ops[-1], 'in_'))
-                res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
-            else:
-                res, res_geom = x, (unit['depth'], H, H, s)      # identity, or max_pool2d(1x1, stride) = subsample
-            self.ops.append(unit['conv1'].bind(x, n, H, H, self.bufR1, pre=pre, impl=impl))
-            if ui == 0:
-                self.in_refs.append((self.ops[-1], 'in_'))
-            self.ops.append(unit['conv2'].bind(self.bufR1, n, H, H, self.bufR2, impl=impl))
-            self.ops.append(unit['conv3'].bind(self.bufR2, n, Ho, Ho, y, res=res, res_geom=res_geom, impl=impl))
-            if ui == 0 and 'shortcut' not in unit:
-                self.in_refs.append((self.ops[-1], 'res'))
-            x, y = y, x
-            H = Ho
-            d_in = unit['depth']
+                    self.in_refs += [(self.ops[-1], 'in_hi', 0), (self.ops[-1], 'in_lo', 1)]
+                self.ops.append(unit['conv2'].bind(None, n, H, H, None, inp_split=r1, out_split=r2, impl=impl))
+                last = ui == len(units) - 1
+                nxt = units[ui + 1]['pre'] if not last else next_pre        # the next unit's pre-activation BN (+ReLU)
+                osplit = ys if nxt is not None else None
+                self.ops.append(unit['conv3'].bind(None, n, Ho, Ho, y, inp_split=r2, res=res, res_geom=res_geom, impl=impl,
+                                                   out_split=osplit, post2=(nxt[0], nxt[1], 1) if nxt is not None else None))
+                if ui == 0 and 'shortcut' not in unit:
+                    self.in_refs.append((self.ops[-1], 'res', 2))
+                if last:
+                    self.out_split = osplit
+                x, y = y, x
+                xs, ys = ys, xs
+                H = Ho
+                d_in = unit['depth']
+        else:
+            self.bufR1 = torch.empty(max(1, n * mx_r), **f32)
+            self.bufR2 = torch.empty(max(1, n * mx_r), **f32)
+            for ui, unit in enumerate(units):
+                s = unit['stride']
+                Ho = (H - 1) // s + 1
+                pre = (unit['pre'][0], unit['pre'][1], 0, 1)
+                if 'shortcut' in unit:
+                    self.ops.append(unit['shortcut'].bind(x, n, H, H, self.bufS, pre=pre, impl=impl))
+                    if ui == 0:
+                        self.in_refs.append((self.ops[-1], 'in_', 2))
+                    res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
+                else:
+                    res, res_geom = x, (unit['depth'], H, H, s)      # identity, or max_pool2d(1x1, stride) = subsample
+                self.ops.append(unit['conv1'].bind(x, n, H, H, self.bufR1, pre=pre, impl=impl))
+                if ui == 0:
+                    self.in_refs.append((self.ops[-1], 'in_', 2))
+                self.ops.append(unit['conv2'].bind(self.bufR1, n, H, H, self.bufR2, impl=impl))
+                self.ops.append(unit['conv3'].bind(self.bufR2, n, Ho, Ho, y, res=res, res_geom=res_geom, impl=impl))
+                if ui == 0 and 'shortcut' not in unit:
+                    self.in_refs.append((self.ops[-1], 'res', 2))
+                x, y = y, x
+                H = Ho
+                d_in = unit['depth']
         self.final = x
         self.final_hw = H * H
         self.out_hw, self.out_depth = H, d_in
         self.in_buf = self.bufA               # stage input when root=False
 
-    def set_input(self, t):
-        """Point the stage at an external input feature map [n, in_hw, in_hw, in_depth] (no copy)."""
-        for op, field in self.in_refs:
-            setattr(op.d, field, t.data_ptr())
-            op.keep = op.keep + (t,)
+    def set_input(self, t, t_split=None):
+        """Point the stage at an external input feature map [n, in_hw, in_hw, in_depth] (fp32 `t`, and in split mode its
+        pre-activated fp16 pair `t_split`); no copy."""
+        srcs = (t_split[0] if t_split else None, t_split[1] if t_split else None, t)
+        for op, field, which in self.in_refs:
+            src = srcs[which]
+            if src is None:
+                raise _lib.HDError('stage input %s missing' % field)
+            setattr(op.d, field, src.data_ptr())
+            op.keep = op.keep + (src,)
 
-    def set_output(self, t):
-        """Let the last unit write its output feature map [n, out_hw, out_hw, out_depth] straight into `t`."""
+    def set_output(self, t, t_split=None):
+        """Let the last unit write its output feature map [n, out_hw, out_hw, out_depth] straight into `t` (and, in split
+        mode, the next stage's pre-activated pair into `t_split`)."""
         op = self.ops[-1]
         op.d.out = t.data_ptr()
         op.keep = op.keep + (t,)
+        if t_split is not None:
+            op.d.out_hi, op.d.out_lo = t_split[0].data_ptr(), t_split[1].data_ptr()
+            op.keep = op.keep + tuple(t_split)
         self.final = t
 
     def run(self, images, out, stream=None):
@@ -302,7 +372,11 @@ class ResNetPlan(object):
             else:
                 check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
                       'hd_conv1_7x7s2')
-            check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64, st), 'hd_maxpool3x3s2_same')
+            ps = self.pool_split
+            check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64,
+                                           fptr(ps[0]) if ps else None, fptr(ps[1]) if ps else None,
+                                           C.c_void_p(ps[2][0].data_ptr()) if ps else None,
+                                           C.c_void_p(ps[2][1].data_ptr()) if ps else None, st), 'hd_maxpool3x3s2_same')
         for op in self.ops:
             op.run(st)
         if self.tail:

@@ -51,7 +51,7 @@ void hd_launch_count_reset(void);
  *   v = acc*post_scale[co] + post_shift[co]   (NULL scale = 1, NULL shift = 0)
  *   if res: v += res[(n*res_H + oy*res_stride)*res_W + ox*res_stride][co]
  *   if post_relu: v = max(v,0)
- *   out[(n*Ho+oy)*Wo+ox][co] = v
+ *   out[(n*Ho+oy)*Wo+ox][co] = v          (out may be NULL when out_hi/out_lo are given, see below)
  * ------------------------------------------------------------------------------------------ */
 enum { HD_IMPL_SIMT = 0, HD_IMPL_TC_3XTF32 = 1, HD_IMPL_TC_1XTF32 = 2, HD_IMPL_TC_3XF16 = 3 };
 
@@ -70,6 +70,15 @@ typedef struct {
   float *out;  long long out_ld;
   int impl;
   const void *tmap_hi, *tmap_lo;              /* HOST pointers to 128-byte CUtensorMap blobs from hd_make_weight_tmap */
+  /* Pre-split activations (impl 3 only).  When in_hi/in_lo are set the A operand is read from two fp16 arrays of the
+   * same [pixels, in_ld] geometry as `in` (hi = RN_f16(a), lo = RN_f16((a - hi) * 2^11), a = the ALREADY pre-activated
+   * input) with cp.async straight into the swizzled tile -- no register staging, no prologue (pre_scale must be NULL).
+   * When out_hi/out_lo are set the epilogue additionally (or, with out == NULL, only) writes
+   *   y = v * post2_scale[co] + post2_shift[co]; if post2_relu: y = max(y, 0)      (NULL scale/shift = 1 / 0)
+   * as such a pair [pixels, out2_ld]: the next layer's pre-activated, pre-split A operand. */
+  const void *in_hi, *in_lo;
+  void *out_hi, *out_lo;  long long out2_ld;
+  const float *post2_scale, *post2_shift;  int post2_relu;
 } hd_conv_desc;
 
 int hd_conv_gemm(const hd_conv_desc *d, void *stream);
@@ -85,8 +94,11 @@ int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int box_rows, int
 /* ---- ResNet root / tail pieces (slim resnet_v2_50, called from src/models.py:65-74) ---- */
 /* conv1: 7x7 stride 2, explicit zero pad 3+3, + bias.  in [N,H,W,3] -> out [N,H/2,W/2,64]; w [7*7*3,64]. */
 int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *out, int N, int H, int W, void *stream);
-/* pool1: 3x3 stride 2 max pool, TF SAME padding (pad 0 top/left, 1 bottom/right for even sizes). */
-int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, void *stream);
+/* pool1: 3x3 stride 2 max pool, TF SAME padding (pad 0 top/left, 1 bottom/right for even sizes).
+ * Optional second output (out_hi/out_lo non-NULL): relu(v*scale[c] + shift[c]) as an fp16 head/remainder pair
+ * (the first bottleneck unit's pre-activation, pre-split for the tensor-core kernel). */
+int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, const float *scale, const float *shift,
+                         void *out_hi, void *out_lo, void *stream);
 /* postnorm BN+ReLU then global mean over HxW: in [N,HW,C] -> out [N,C]. */
 int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, float *out, int N, int HW, int C, void *stream);
 

@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_layouts_match_header_sizes():
     """hd_conv_desc / hd_smpl_consts mirrors: field counts and natural-alignment sizes."""
     from human_dynamics_b200 import _lib
-    assert ctypes.sizeof(_lib.ConvDesc) == 216
+    assert ctypes.sizeof(_lib.ConvDesc) == 280
     assert ctypes.sizeof(_lib.SmplConsts) == 16 + 9 * 8 + 24 * 4
     assert _lib.ConvDesc.in_ld.offset == 8 and _lib.ConvDesc.w_kn.offset == 64 and _lib.ConvDesc.out.offset == 176
 
@@ -63,3 +63,24 @@ def test_invalid_arguments_return_status_not_crash():
     assert b'null' in _lib.lib.hd_last_error()
     assert _lib.lib.hd_rodrigues(None, None, 4, None) == 1
     assert _lib.lib.hd_smpl_workspace_bytes(10) >= 10 * 24 * 21 * 4
+
+
+def test_conv_desc_matches_compiled_struct():
+    """Compile a one-liner against include/hd_b200.h with gcc and compare sizeof/offsetof with the ctypes mirror."""
+    import subprocess, tempfile, shutil
+    from human_dynamics_b200 import _lib
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('gcc not available')
+    fields = ['in_ld', 'w_kn', 'Cout', 'pre_scale', 'post_relu', 'res', 'out', 'impl', 'tmap_hi', 'in_hi', 'out_hi', 'out2_ld',
+              'post2_relu']
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "hd_b200.h"\nint main(){printf("%zu %zu", sizeof(hd_conv_desc), sizeof(hd_smpl_consts));\n'
+    src += ''.join('printf(" %%zu", offsetof(hd_conv_desc, %s));\n' % f for f in fields) + 'return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, 't.c'); exe = os.path.join(td, 't')
+        open(c, 'w').write(src)
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
+        out = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert out[0] == ctypes.sizeof(_lib.ConvDesc) and out[1] == ctypes.sizeof(_lib.SmplConsts)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(_lib.ConvDesc, f).offset == off, f
