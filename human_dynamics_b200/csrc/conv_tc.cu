@@ -118,10 +118,10 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_LD = BN + 4;                          // padded row of the epilogue staging tile (floats)
-  static constexpr int STG_ROWS = 8;                            // rows staged per warp per pass
+  static constexpr int SLAB = 32;                               // accumulator columns transposed per epilogue pass
+  static constexpr int STG_LD = SLAB + 4;                       // padded row of the per-warp 32 x 32 staging tile (floats)
   static constexpr int STG_OFFSET = BAR_OFFSET + 128;
-  static constexpr int STG_BYTES = 4 * STG_ROWS * STG_LD * 4;   // 4 drain warps
+  static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;         // 4 drain warps
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
   static constexpr int SMEM_BYTES = LUT_OFFSET + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
@@ -402,9 +402,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
-    float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::STG_ROWS * C::STG_LD);
-    constexpr int CPL = BN / 32;                 // consecutive columns per lane in the coalesced phase (4 or 2)
-    const int col = lane * CPL;
+    float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (32 * C::STG_LD);
     const int hw = p.Ho * p.Wo;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -412,6 +410,20 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       float sums[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) sums[i] = 0.f;
+      if (p.res && p.vec_out) {       // pull this tile's residual rows towards L2 while the main loop runs
+        const int m = m0 + warp * 32 + lane;
+        if (m < p.M) {
+          size_t rrow = (size_t)m;
+          if (!(p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo)) {
+            const int n = m / hw;
+            const int rr = m - n * hw;
+            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+            rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+          }
+          const float *rp = p.res + rrow * p.res_ld + n0;
+          for (int c = 0; c < BN && n0 + c < p.Cout; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
+        }
+      }
       for (int g = 0; g < num_g; ++g) {
         const int G = ti * num_g + g;
         const int b = G & 1;
@@ -444,95 +456,93 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         if (lane == 0) mbar_arrive(smallf_bar(sb));
       }
       long long te0 = prof ? clock64() : 0;
-      // Epilogue (overlaps the next tile's main loop).  Each lane owns one accumulator ROW (TMEM lane), but global
-      // memory wants a warp to touch one row's contiguous columns at a time: transpose through a small padded smem
-      // tile, 8 rows per pass; every warp-level access below is BN*4 contiguous bytes (residual load, output store).
-      const int co = n0 + col;
-      const bool cvalid = co < p.Cout;
-      float psc[CPL], psh[CPL];
-#pragma unroll
-      for (int e = 0; e < CPL; ++e) {
-        psc[e] = (p.post_scale && co + e < p.Cout) ? __ldg(p.post_scale + co + e) : 1.0f;
-        psh[e] = (p.post_shift && co + e < p.Cout) ? __ldg(p.post_shift + co + e) : 0.0f;
-      }
+      // Epilogue (overlaps the next tile's main loop).  Each lane owns one accumulator ROW (TMEM lane) but global memory
+      // wants a warp to touch contiguous columns of a row.  Per 32-column slab: the residual slab is fetched by cp.async
+      // straight into the warp's padded 32 x 32 smem tile (no registers), every lane adds its 32 accumulator values into its
+      // row of the tile, then the warp walks the tile 4 rows x 128 contiguous bytes per access: shift (+ReLU), fp32 store
+      // and/or the next layer's pre-activated fp16 head/remainder pair.  The loops are kept rolled on purpose: this code runs
+      // once per tile on four warps, so its size (instruction-cache misses) is what it costs.
+      const int rq = lane >> 3, c4 = (lane & 7) * 4;       // coalesced phase: row rq + 4*i of the warp's 32, columns c4..c4+3 of the slab
+      const bool res_plain = p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo;
+      const bool res_smem = p.res != nullptr && p.vec_out;
 #pragma unroll 1
-      for (int pass = 0; pass < 32 / C::STG_ROWS; ++pass) {
-        // residual rows of this pass first (8 independent coalesced loads in flight), then the math and the stores
-        float rres[C::STG_ROWS][CPL];
-        if (p.res && p.vec_out && cvalid) {
-#pragma unroll
-          for (int r = 0; r < C::STG_ROWS; ++r) {
-            const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
-#pragma unroll
-            for (int e = 0; e < CPL; ++e) rres[r][e] = 0.f;
-            if (m < p.M) {
+      for (int sl = 0; sl < BN / C::SLAB; ++sl) {
+        const int co = n0 + sl * C::SLAB + c4;
+        const bool cvalid = co < p.Cout;
+        __syncwarp();
+        if (res_smem) {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int row = rq + 4 * i;
+            const int m = m0 + warp * 32 + row;
+            const bool ok = m < p.M && cvalid;
+            size_t rrow = (size_t)(ok ? m : 0);
+            if (ok && !res_plain) {
               const int n = m / hw;
               const int rr = m - n * hw;
               const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-              const float *rp = p.res + (((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride) * p.res_ld + co;
-              if (CPL == 4) {
-                const float4 rv = __ldg(reinterpret_cast<const float4 *>(rp));
-                rres[r][0] = rv.x; rres[r][1] = rv.y; rres[r][CPL - 2] = rv.z; rres[r][CPL - 1] = rv.w;
-              } else {
-                const float2 rv = __ldg(reinterpret_cast<const float2 *>(rp));
-                rres[r][0] = rv.x; rres[r][1] = rv.y;
-              }
+              rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
             }
+            cp_async16(smem_u32(stg + row * C::STG_LD + c4), p.res + rrow * p.res_ld + (ok ? co : 0), (ok && !(xmode & 16)) ? 16u : 0u);
           }
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncwarp();
+        }
+        float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 qsc = psc, qsh = psh;
+        if (p.vec_out && cvalid) {
+          if (p.post_scale && !res_smem) psc = __ldg(reinterpret_cast<const float4 *>(p.post_scale + co));
+          if (p.post_shift) psh = __ldg(reinterpret_cast<const float4 *>(p.post_shift + co));
+          if (p.out_hi && p.post2_scale) qsc = __ldg(reinterpret_cast<const float4 *>(p.post2_scale + co));
+          if (p.out_hi && p.post2_shift) qsh = __ldg(reinterpret_cast<const float4 *>(p.post2_shift + co));
+        }
+        // thread = row: accumulator slab (+ residual already sitting in the tile) -> tile.  sums[] needs compile-time indices.
+#pragma unroll
+        for (int c = 0; c < C::SLAB; c += 4) {
+          float4 v;
+#pragma unroll
+          for (int k = 0; k < BN / C::SLAB; ++k)
+            if (k == sl) v = make_float4(sums[k * C::SLAB + c], sums[k * C::SLAB + c + 1], sums[k * C::SLAB + c + 2], sums[k * C::SLAB + c + 3]);
+          float4 *tp = reinterpret_cast<float4 *>(stg + lane * C::STG_LD + c);
+          if (res_smem) {
+            if (p.post_scale) {      // (rare: scale and residual together) scale before the residual add, broadcast loads
+              const int cc = n0 + sl * C::SLAB + c;
+              if (cc < p.Cout) {
+                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.post_scale + cc));
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+              }
+            }
+            const float4 r = *tp;
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+          }
+          *tp = v;
         }
         __syncwarp();
-        if ((lane / C::STG_ROWS) == pass) {        // the 8 lanes whose rows are staged in this pass
-          float *dst = stg + (lane % C::STG_ROWS) * C::STG_LD;
-#pragma unroll
-          for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(sums[c], sums[c + 1], sums[c + 2], sums[c + 3]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < C::STG_ROWS; ++r) {
-          const int m = m0 + warp * 32 + pass * C::STG_ROWS + r;
-          if (m >= p.M) break;                     // warp-uniform
-          float x[CPL];
-#pragma unroll
-          for (int e = 0; e < CPL; ++e) x[e] = stg[r * C::STG_LD + col + e] * psc[e] + psh[e];
-          if (!cvalid) continue;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int row = rq + 4 * i;
+          const int m = m0 + warp * 32 + row;
+          if (m >= p.M || !cvalid) continue;
+          const float4 a = *reinterpret_cast<const float4 *>(stg + row * C::STG_LD + c4);
           if (p.vec_out) {
-            if (p.res) {
-#pragma unroll
-              for (int e = 0; e < CPL; ++e) x[e] += rres[r][e];
+            float x0 = a.x * psc.x + psh.x, x1 = a.y * psc.y + psh.y, x2 = a.z * psc.z + psh.z, x3 = a.w * psc.w + psh.w;
+            if (p.post_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+            if (p.out && !(xmode & 8)) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x0, x1, x2, x3);
+            if (p.out_hi && !(xmode & 32)) {      // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
+              float y0 = x0 * qsc.x + qsh.x, y1 = x1 * qsc.y + qsh.y, y2 = x2 * qsc.z + qsh.z, y3 = x3 * qsc.w + qsh.w;
+              if (p.post2_relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+              const __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+              const __half2 l0 = __floats2half2_rn((y0 - f0.x) * 2048.0f, (y1 - f0.y) * 2048.0f);
+              const __half2 l1 = __floats2half2_rn((y2 - f1.x) * 2048.0f, (y3 - f1.y) * 2048.0f);
+              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.out_hi) + (size_t)m * p.out2_ld + co) =
+                  make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.out_lo) + (size_t)m * p.out2_ld + co) =
+                  make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
             }
-            if (p.post_relu) {
-#pragma unroll
-              for (int e = 0; e < CPL; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            if (p.out) {
-              if (CPL == 4) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x[0], x[1], x[CPL - 2], x[CPL - 1]);
-              else *reinterpret_cast<float2 *>(p.out + (size_t)m * p.out_ld + co) = make_float2(x[0], x[1]);
-            }
-            if (p.out_hi) {      // the next layer's A operand: second affine (+ReLU) = its pre-activation, pre-split into fp16 head/remainder
-              uint32_t hp[CPL / 2], lp[CPL / 2];
-#pragma unroll
-              for (int e = 0; e < CPL; e += 2) {
-                float y0 = x[e], y1 = x[e + 1];
-                if (p.post2_scale) { y0 *= __ldg(p.post2_scale + co + e); y1 *= __ldg(p.post2_scale + co + e + 1); }
-                if (p.post2_shift) { y0 += __ldg(p.post2_shift + co + e); y1 += __ldg(p.post2_shift + co + e + 1); }
-                if (p.post2_relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-                const __half2 hh = __floats2half2_rn(y0, y1);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn((y0 - hf.x) * 2048.0f, (y1 - hf.y) * 2048.0f);
-                hp[e / 2] = *reinterpret_cast<const uint32_t *>(&hh);
-                lp[e / 2] = *reinterpret_cast<const uint32_t *>(&ll);
-              }
-              __half *oh = reinterpret_cast<__half *>(p.out_hi) + (size_t)m * p.out2_ld + co;
-              __half *ol = reinterpret_cast<__half *>(p.out_lo) + (size_t)m * p.out2_ld + co;
-              if (CPL == 4) {
-                *reinterpret_cast<uint2 *>(oh) = make_uint2(hp[0], hp[CPL / 2 - 1]);
-                *reinterpret_cast<uint2 *>(ol) = make_uint2(lp[0], lp[CPL / 2 - 1]);
-              } else {
-                *reinterpret_cast<uint32_t *>(oh) = hp[0];
-                *reinterpret_cast<uint32_t *>(ol) = lp[0];
-              }
-            }
-          } else {
+          } else {             // ragged / unaligned outputs (IEF 85- and 72-wide heads): element-wise
+            const float av[4] = {a.x, a.y, a.z, a.w};
             size_t res_row = 0;
             if (p.res) {
               const int n = m / hw;
@@ -541,9 +551,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
               res_row = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
             }
 #pragma unroll
-            for (int e = 0; e < CPL; ++e) {
+            for (int e = 0; e < 4; ++e) {
               if (co + e >= p.Cout) continue;
-              float y = x[e];
+              float y = av[e];
+              if (p.post_scale) y *= __ldg(p.post_scale + co + e);
+              if (p.post_shift) y += __ldg(p.post_shift + co + e);
               if (p.res) y += p.res[res_row * p.res_ld + co + e];
               if (p.post_relu) y = fmaxf(y, 0.f);
               p.out[(size_t)m * p.out_ld + co + e] = y;

@@ -10,6 +10,7 @@ NAMES = ['prod_loop', 'prod_wait_empty', 'drain_loop', 'drain_wait_accf', 'epilo
 dev = torch.device('cuda')
 rng = np.random.RandomState(0)
 cases = [  # n, H, Cin, Cout, k, stride, residual, pre
+    (32, 56, 64, 256, 1, 1, True, False),
     (48, 14, 256, 256, 3, 1, False, False),
     (32, 28, 128, 128, 3, 1, False, False),
     (32, 56, 64, 256, 1, 1, True, False),
@@ -24,7 +25,12 @@ for n, H, Cin, Cout, k, s, res, pre in cases:
     out = torch.empty((n, H, H, Cout), device=dev)
     r = torch.randn((n, H, H, Cout), device=dev) if res else None
     pr = (torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev), 0, 1) if pre else None
-    op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl=os.environ.get('HD_IMPL', 'tc3h'))
+    if os.environ.get('HD_SPLIT', '0') == '1' and not pre:
+        xs = (x.half(), ((x - x.half().float()) * 2048).half())
+        osp = (torch.empty((n, H, H, Cout), dtype=torch.float16, device=dev), torch.empty((n, H, H, Cout), dtype=torch.float16, device=dev))
+        op = pc.bind(None, n, H, H, out if res else None, inp_split=xs, out_split=osp, res=r, impl='tc3h')
+    else:
+        op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl=os.environ.get('HD_IMPL', 'tc3h'))
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     modes = [int(a) for a in sys.argv[1:]] or [0]
     for mode in modes:
@@ -35,7 +41,7 @@ for n, H, Cin, Cout, k, s, res, pre in cases:
         torch.cuda.synchronize()
         if mode:
             d = dbg.cpu().numpy()
-            print('   [xmode %d: 1=no A STS, 2=no B TMA, 4=no A loads]  ' % mode + '  '.join('%s=%d' % (nm, v) for nm, v in zip(NAMES, d)))
+            print('   [xmode %d: 1=no A STS, 2=no B TMA, 4=no A loads, 8=no fp32 store, 16=no res load, 32=no split store]  ' % mode + '  '.join('%s=%d' % (nm, v) for nm, v in zip(NAMES, d)))
     dbg = torch.zeros(16, dtype=torch.int64, device=dev)
     for _ in range(2):
         check(lib.hd_conv_gemm_profile(op.ref, st, C.c_void_p(dbg.data_ptr())))
