@@ -32,9 +32,8 @@
 namespace hd {
 namespace {
 
-constexpr int BM = 128, STAGES = 3;
+constexpr int BM = 128;
 constexpr int A_TILE_BYTES = BM * 128;      // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 fp16 of K)
-constexpr int NUM_THREADS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -112,8 +111,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-template <int BN, bool HALF>
+template <int BN, bool HALF, bool DUAL = false>
 struct Cfg {
+  // DUAL (epilogue-bound layers, K <= 256, one drain group per tile): two drain/epilogue warp groups take alternate tiles;
+  // the main loop is short there, so 2 operand stages suffice and pay for the second set of staging tiles.
+  static constexpr int STAGES = DUAL ? 2 : 3;
+  static constexpr int DW = DUAL ? 8 : 4;                       // drain + epilogue warps
+  static constexpr int NUM_THREADS = (DW + 8 + 4) * 32;         // + 8 producer warps + {TMA, MMA, 2 idle}
   static constexpr int BKE = HALF ? 64 : 32;                    // K elements per chunk (one 128-byte row)
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -121,7 +125,7 @@ struct Cfg {
   static constexpr int SLAB = 32;                               // accumulator columns transposed per epilogue pass
   static constexpr int STG_LD = SLAB + 4;                       // padded row of the per-warp 32 x 32 staging tile (floats)
   static constexpr int STG_OFFSET = BAR_OFFSET + 128;
-  static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;         // 4 drain warps
+  static constexpr int STG_BYTES = DW * 32 * STG_LD * 4;        // one 32 x 32 tile per drain warp
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
   static constexpr int SMEM_BYTES = LUT_OFFSET + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
@@ -136,11 +140,12 @@ struct RowState {       // 4 output rows of one producer thread: image index and
   int n[4], iy[4], ix[4];
 };
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT, bool DUAL>
+__global__ void __launch_bounds__((Cfg<BN, HALF, DUAL>::NUM_THREADS), 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
-  using C = Cfg<BN, HALF>;
-  constexpr int BKE = C::BKE, PF = C::PF, V = C::V;
+  using C = Cfg<BN, HALF, DUAL>;
+  constexpr int BKE = C::BKE, PF = C::PF, V = C::V, STAGES = C::STAGES, DW = C::DW, NUM_THREADS = C::NUM_THREADS;
+  constexpr int W_TMA = DW + 8, W_MMA = DW + 9;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -154,7 +159,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (GATHER ? p.K_pad : p.K) / BKE;   // GATHER: ragged Cin (conv1: K=147 zero-padded to 192)
-  const int num_g = (num_k + PCH - 1) / PCH;          // drain groups per tile
+  const int num_g = (num_k + PCH - 1) / PCH;          // drain groups per tile (DUAL: host guarantees 1)
   const int tiles_n = (p.Cout + BN - 1) / BN;
   const int num_tiles = ((p.M + BM - 1) / BM) * tiles_n;
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -171,7 +176,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == W_TMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -195,10 +200,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   const int xmode = p.dbg ? (int)p.dbg[15] : 0;      // timing experiments (hd_conv_gemm_profile only; results invalid)
   // TMEM columns: [0,BN) cross terms 0, [BN,2BN) cross terms 1, [2BN,3BN) main 0, [3BN,4BN) main 1
 
-  if (warp >= 4 && warp < 12) {
+  if (warp >= DW && warp < DW + 8) {
     // =============================== A producers (256 threads) ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
-    const int t = threadIdx.x - 128;      // 0..255
+    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int t = threadIdx.x - DW * 32;  // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
     const int rb = t >> 3;                // rows rb + 32*i, i < 4
     const uint32_t sw_off = (uint32_t)((j ^ (rb & 7)) << 4);
@@ -396,22 +402,24 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
     }   // !ASPLIT
-  } else if (warp < 4) {
+  } else if (warp < DW) {
     // =============================== drain + epilogue ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int dgroup = warp >> 2, quarter = warp & 3;     // DUAL: group 0 takes even tiles, group 1 odd tiles
+    if (DUAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
     float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (32 * C::STG_LD);
     const int hw = p.Ho * p.Wo;
-    for (int ti = 0; ti < my_tiles; ++ti) {
+    for (int ti = dgroup; ti < my_tiles; ti += (DUAL ? 2 : 1)) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       float sums[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) sums[i] = 0.f;
       if (p.res && p.vec_out) {       // pull this tile's residual rows towards L2 while the main loop runs
-        const int m = m0 + warp * 32 + lane;
+        const int m = m0 + quarter * 32 + lane;
         if (m < p.M) {
           size_t rrow = (size_t)m;
           if (!(p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo)) {
@@ -471,10 +479,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         const bool cvalid = co < p.Cout;
         __syncwarp();
         if (res_smem) {
-#pragma unroll 1
+#pragma unroll 4
           for (int i = 0; i < 8; ++i) {
             const int row = rq + 4 * i;
-            const int m = m0 + warp * 32 + row;
+            const int m = m0 + quarter * 32 + row;
             const bool ok = m < p.M && cvalid;
             size_t rrow = (size_t)(ok ? m : 0);
             if (ok && !res_plain) {
@@ -519,10 +527,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           *tp = v;
         }
         __syncwarp();
-#pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
+#pragma unroll 4
+        for (int i = 0; i < 8; ++i) {      // 4 independent rows in flight per lane: this loop is latency-, not issue-bound
           const int row = rq + 4 * i;
-          const int m = m0 + warp * 32 + row;
+          const int m = m0 + quarter * 32 + row;
           if (m >= p.M || !cvalid) continue;
           const float4 a = *reinterpret_cast<const float4 *>(stg + row * C::STG_LD + c4);
           if (p.vec_out) {
@@ -567,8 +575,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     if (prof) { p.dbg[2] = clock64() - t_start; p.dbg[3] = t_wait; p.dbg[4] = t_epi; }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 12) {
+    // register pool = threads x launch allocation (512 x 128, or 640 x 96 for DUAL); the budgets below must fit in it or
+    // setmaxnreg.inc never returns:  4-warp: 128*200 + 256*136 + 128*40 = 65536;  DUAL: 256*168 + 256*56 + 128*24 = 60416 <= 61440
+    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == W_TMA) {
       // =============================== B producer (TMA) ===============================
       if (lane == 0) {
         const bool prof = p.dbg != nullptr && blockIdx.x == 0;
@@ -592,7 +603,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         }
         if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
       }
-    } else if (warp == 13) {
+    } else if (warp == W_MMA) {
       // =============================== MMA issuer ===============================
       if (lane == 0) {
         const bool prof = p.dbg != nullptr && blockIdx.x == 0;
@@ -649,7 +660,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 12) {
+  if (warp == W_TMA) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(C::TMEM_COLS));
   }
@@ -673,12 +684,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false, bool DUAL = false>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
-  using C = Cfg<BN, HALF>;
+  using C = Cfg<BN, HALF, DUAL>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
     configured = true;
   }
@@ -694,7 +705,7 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   }
   const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
   dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
-  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL><<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -716,6 +727,8 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       set_last_error_text("hd_conv_gemm(tc split-A): needs Cin % 64 == 0, in_ld % 8 == 0, aligned in_hi/in_lo, no prologue");
       return HD_ERR_INVALID;
     }
+    if (p.K <= 256)      // epilogue-bound layers: one drain group per tile (<= 16 MMAs per accumulator), two drain/epilogue warp groups
+      return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);
     return p.Cout <= 64 ? launch_tc<64, true, 2, true, false, true>(p, d, st) : launch_tc<128, true, 2, true, false, true>(p, d, st);
   }
   if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded
