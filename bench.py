@@ -100,7 +100,9 @@ def cpu_reference_run(workload, steps, warmup, clips_per_step=1, T=20):
     import torch
     from human_dynamics_b200 import synthetic
     from oracle import nets_ref
-    cores = os.cpu_count() or 1
+    # measured on this pool's 128-core host (tools/cpu_threads.py): the torch-CPU port peaks at 16-32 threads (51 frames/s
+    # for the ResNet part) and collapses beyond 64 (<1 frame/s at 128), so the reference arm uses min(cores, 32) threads.
+    cores = min(os.cpu_count() or 1, int(os.environ.get('HD_CPU_THREADS', '32')))
     torch.set_num_threads(cores)
     w = synthetic.make_synthetic_weights(seed=1)
     smpl = synthetic.make_synthetic_smpl(seed=2)
