@@ -367,7 +367,15 @@ def measure_roofline(args, peaks, env):
     ach = tc_flops / tc_time / 1e12
     peak = peaks['bf16_tflops_sustained']
     step_s = env['ms'] * 1e-3
-    return {'bound': 'tensor', 'kernel': kind, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and args.mode in ('auto', 'tc3h'):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = {'dram_bytes_per_launch': tj['tensor_bound_launch']['dram_bytes'],
+                   'algorithmic_bytes_per_launch': tj['tensor_bound_launch']['algorithmic_bytes'],
+                   'launch': tj['tensor_bound_launch']['layer'], 'source': 'profiles/r01_traffic.json (one ncu --set full capture)'}
+    return {'bound': 'tensor', 'kernel': kind, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
             'launches_per_step': n_tc, 'avg_launch_us': tc_time / n_tc * 1e6, 'algorithmic_flops_per_launch_avg': tc_flops / n_tc,
             'share_of_step': tc_time / step_s,
             'note': 'algorithmic FLOPs (2*M*N*K, dense, as the reference computes them) of the %d conv launches of one step / their '

@@ -15,7 +15,12 @@ x = torch.randn((n, H, H, Cin), device=dev)
 out = torch.empty((n, H, H, Cout), device=dev)
 r = torch.randn((n, H, H, Cout), device=dev) if res else None
 pr = (torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev), 0, 1) if pre else None
-op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl=impl)
+if os.environ.get('HD_SPLIT', '0') == '1':
+    xs = (x.half(), ((x - x.half().float()) * 2048).half())
+    osp = (torch.empty((n, H, H, Cout), dtype=torch.float16, device=dev), torch.empty((n, H, H, Cout), dtype=torch.float16, device=dev))
+    op = pc.bind(None, n, H, H, out if res else None, inp_split=xs, out_split=osp, res=r, impl='tc3h')
+else:
+    op = pc.bind(x, n, H, H, out, pre=pr, res=r, impl=impl)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(4):
     op.run(st)
