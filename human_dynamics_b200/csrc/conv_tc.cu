@@ -166,7 +166,8 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 9);     // 8 producer warps + 1 arrive.expect_tx from the TMA lane
+      mbar_init(full_bar(s), ASPLIT ? 257 : 9);   // 8 producer warps (ASPLIT: 256 threads, hardware arrive per thread when its cp.asyncs land)
+                                                  // + 1 arrive.expect_tx from the TMA lane
       mbar_init(empty_bar(s), 1);    // tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
@@ -235,7 +236,6 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       const __half *ilo = reinterpret_cast<const __half *>(p.in_lo);
       RowState rs;
       int kc = 0, ti = 0;
-      constexpr int LAG = STAGES - 1;        // chunk q is signalled after chunk q+LAG has been issued
       for (int q = 0; q < total; ++q) {
         if (kc == 0) enter_tile(ti, rs);
         const int s = q % STAGES;
@@ -256,20 +256,14 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           cp_async16(a_hi + off, ihi + e, ok ? 16u : 0u);
           cp_async16(a_lo + off, ilo + e, ok ? 16u : 0u);
         }
-        cp_async_commit();
-        if (q >= LAG) {
-          cp_async_wait<LAG>();
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar((q - LAG) % STAGES));
-        }
+        // the barrier itself is told to arrive (without a pending-count increment) once this thread's copies have landed:
+        // chunks are published the moment their data is in smem, with no producer thread in the loop, so up to STAGES
+        // chunks are genuinely in flight.  The MMA thread issues the generic->async proxy fence after its wait.
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
         if (++kc == num_k) { kc = 0; ++ti; }
       }
+      cp_async_commit();
       cp_async_wait<0>();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0)
-        for (int q = (total > LAG ? total - LAG : 0); q < total; ++q) mbar_arrive(full_bar(q % STAGES));
       if (prof) { p.dbg[0] = clock64() - t_start; p.dbg[1] = t_wait; }
     } else {
     RowState pf_rs, st_rs;                 // prefetch-side and store-side row state (may be one tile apart)
@@ -627,6 +621,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             long long tw1 = prof ? clock64() : 0;
             mbar_wait(full_bar(s), ph);
             if (prof) { t_wacc += tw1 - tw0; t_wfull += clock64() - tw1; }
+            if (ASPLIT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) data -> UMMA (async proxy)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_big = tmem_d + (uint32_t)(BN * (2 + b));
             const uint32_t a_hi = smem_base + s * C::STAGE_BYTES;
