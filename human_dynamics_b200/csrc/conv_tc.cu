@@ -467,25 +467,37 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       const int rq = lane >> 3, c4 = (lane & 7) * 4;       // coalesced phase: row rq + 4*i of the warp's 32, columns c4..c4+3 of the slab
       const bool res_plain = p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo;
       const bool res_smem = p.res != nullptr && p.vec_out;
-#pragma unroll 1
+#pragma unroll
       for (int sl = 0; sl < BN / C::SLAB; ++sl) {
         const int co = n0 + sl * C::SLAB + c4;
         const bool cvalid = co < p.Cout;
         __syncwarp();
+        const int mrow0 = m0 + quarter * 32 + rq;           // this lane's first row of the slab; its rows are mrow0 + 4*i
         if (res_smem) {
-#pragma unroll 4
-          for (int i = 0; i < 8; ++i) {
-            const int row = rq + 4 * i;
-            const int m = m0 + quarter * 32 + row;
-            const bool ok = m < p.M && cvalid;
-            size_t rrow = (size_t)(ok ? m : 0);
-            if (ok && !res_plain) {
-              const int n = m / hw;
-              const int rr = m - n * hw;
-              const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-              rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+          const uint32_t tdst = smem_u32(stg + rq * C::STG_LD + c4);
+          if (res_plain) {                                    // residual row == output row: step a pointer, no index math
+            const float *rp = p.res + (size_t)mrow0 * p.res_ld + (cvalid ? co : 0);
+            const size_t rstep = 4 * (size_t)p.res_ld;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = cvalid && (mrow0 + 4 * i) < p.M;
+              cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), ok ? (const void *)(rp + i * rstep) : (const void *)p.res,
+                         (ok && !(xmode & 16)) ? 16u : 0u);
             }
-            cp_async16(smem_u32(stg + row * C::STG_LD + c4), p.res + rrow * p.res_ld + (ok ? co : 0), (ok && !(xmode & 16)) ? 16u : 0u);
+          } else {
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + 4 * i;
+              const bool ok = m < p.M && cvalid;
+              size_t rrow = 0;
+              if (ok) {
+                const int n = m / hw;
+                const int rr = m - n * hw;
+                const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+                rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+              }
+              cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), p.res + rrow * p.res_ld + (ok ? co : 0), (ok && !(xmode & 16)) ? 16u : 0u);
+            }
           }
           cp_async_commit();
           cp_async_wait<0>();
@@ -502,10 +514,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         // thread = row: accumulator slab (+ residual already sitting in the tile) -> tile.  sums[] needs compile-time indices.
 #pragma unroll
         for (int c = 0; c < C::SLAB; c += 4) {
-          float4 v;
-#pragma unroll
-          for (int k = 0; k < BN / C::SLAB; ++k)
-            if (k == sl) v = make_float4(sums[k * C::SLAB + c], sums[k * C::SLAB + c + 1], sums[k * C::SLAB + c + 2], sums[k * C::SLAB + c + 3]);
+          float4 v = make_float4(sums[sl * C::SLAB + c], sums[sl * C::SLAB + c + 1], sums[sl * C::SLAB + c + 2], sums[sl * C::SLAB + c + 3]);
           float4 *tp = reinterpret_cast<float4 *>(stg + lane * C::STG_LD + c);
           if (res_smem) {
             if (p.post_scale) {      // (rare: scale and residual together) scale before the residual add, broadcast loads
@@ -521,26 +530,31 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           *tp = v;
         }
         __syncwarp();
+        const float *tsrc = stg + rq * C::STG_LD + c4;
+        float *op = p.out ? p.out + (size_t)mrow0 * p.out_ld + co : nullptr;
+        __half *ohp = p.out_hi ? reinterpret_cast<__half *>(p.out_hi) + (size_t)mrow0 * p.out2_ld + co : nullptr;
+        __half *olp = p.out_hi ? reinterpret_cast<__half *>(p.out_lo) + (size_t)mrow0 * p.out2_ld + co : nullptr;
+        const size_t ostep = 4 * (size_t)p.out_ld, hstep = 4 * (size_t)p.out2_ld;
+        const bool st32 = op != nullptr && !(xmode & 8), st16 = ohp != nullptr && !(xmode & 32);
 #pragma unroll 4
         for (int i = 0; i < 8; ++i) {      // 4 independent rows in flight per lane: this loop is latency-, not issue-bound
-          const int row = rq + 4 * i;
-          const int m = m0 + quarter * 32 + row;
+          const int m = mrow0 + 4 * i;
           if (m >= p.M || !cvalid) continue;
-          const float4 a = *reinterpret_cast<const float4 *>(stg + row * C::STG_LD + c4);
+          const float4 a = *reinterpret_cast<const float4 *>(tsrc + i * 4 * C::STG_LD);
           if (p.vec_out) {
             float x0 = a.x * psc.x + psh.x, x1 = a.y * psc.y + psh.y, x2 = a.z * psc.z + psh.z, x3 = a.w * psc.w + psh.w;
             if (p.post_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-            if (p.out && !(xmode & 8)) *reinterpret_cast<float4 *>(p.out + (size_t)m * p.out_ld + co) = make_float4(x0, x1, x2, x3);
-            if (p.out_hi && !(xmode & 32)) {      // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
+            if (st32) *reinterpret_cast<float4 *>(op + i * ostep) = make_float4(x0, x1, x2, x3);
+            if (st16) {          // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
               float y0 = x0 * qsc.x + qsh.x, y1 = x1 * qsc.y + qsh.y, y2 = x2 * qsc.z + qsh.z, y3 = x3 * qsc.w + qsh.w;
               if (p.post2_relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
               const __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
               const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
               const __half2 l0 = __floats2half2_rn((y0 - f0.x) * 2048.0f, (y1 - f0.y) * 2048.0f);
               const __half2 l1 = __floats2half2_rn((y2 - f1.x) * 2048.0f, (y3 - f1.y) * 2048.0f);
-              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.out_hi) + (size_t)m * p.out2_ld + co) =
+              *reinterpret_cast<uint2 *>(ohp + i * hstep) =
                   make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.out_lo) + (size_t)m * p.out2_ld + co) =
+              *reinterpret_cast<uint2 *>(olp + i * hstep) =
                   make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
             }
           } else {             // ragged / unaligned outputs (IEF 85- and 72-wide heads): element-wise
