@@ -293,7 +293,7 @@ def main():
     if rank == 0:
         line = {'metric': metric, 'value': value, 'unit': unit_name, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': {'auto': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)', 'tc3h': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)',
+                'dtype': 'f32 (SMPL; blend GEMM on tcgen05 with the fp16 head/remainder split)' if args.workload == 'smpl' else {'auto': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)', 'tc3h': 'f32 (tcgen05 3x fp16 head/remainder split, fp32 two-level accumulate)',
                           'tc3': 'f32 (tcgen05 3xTF32 split, fp32 two-level accumulate)', 'simt': 'f32', 'tc1': 'tf32'}[args.mode],
                 'data': 'synthetic',
                 'config': {'workload': workload_name(args), 'mode': args.mode, 'frame_chunk': args.frame_chunk, 'late_chunk': args.late_chunk,

@@ -65,6 +65,9 @@ SIGNATURES = {
     'hd_ief_delta_init': (_i, [_vp, _vp, _i, _i, _vp]),
     'hd_smpl_workspace_bytes': (_sz, [_i]),
     'hd_smpl_forward': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    'hd_smpl_pose': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    'hd_smpl_lbs': (_i, [C.POINTER(SmplConsts), _vp, _ll, _vp, _vp, _i, _i, _i, _vp]),
+    'hd_smpl_joints': (_i, [C.POINTER(SmplConsts), _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     'hd_rodrigues': (_i, [_vp, _vp, _i, _vp]),
     'hd_global_rigid': (_i, [_vp, _vp, C.POINTER(C.c_int), _vp, _vp, _i, _i, _vp]),
     'hd_orth_proj': (_i, [_vp, _vp, _vp, _i, _i, _vp]),

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
                                                         const float *__restrict__ J_template,
                                                         const float *__restrict__ J_shapedirs, float *__restrict__ Rs,
                                                         float *__restrict__ Rs_out, float *__restrict__ Jtr,
-                                                        float *__restrict__ A12, int N, int out_mul, int out_off) {
+                                                        float *__restrict__ A12, int N, int out_mul, int out_off,
+                                                        float *__restrict__ coef, int coef_ld) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -120,6 +121,17 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
     if (Jtr) {
       float *o = Jtr + (no * 24 + lane) * 3;
       o[0] = tw[0]; o[1] = tw[1]; o[2] = tw[2];
+    }
+    if (coef) {        // blend-GEMM operand row: [beta(10) | (R_j - I), j = 1..23 (207) | 0 ...]  (batch_smpl.py:110,127-128)
+      float *cr = coef + (size_t)n * coef_ld;
+      if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < 10; ++b) cr[b] = __ldg(beta + (size_t)n * beta_ld + b);
+        for (int k = 217; k < coef_ld; ++k) cr[k] = 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cr[10 + (lane - 1) * 9 + i] = R[i] - ((i == 0 || i == 4 || i == 8) ? 1.0f : 0.0f);
+      }
     }
     float4 *a = reinterpret_cast<float4 *>(A12 + ((size_t)n * 24 + lane) * 12);
 #pragma unroll
@@ -234,6 +246,53 @@ __global__ void __launch_bounds__(128) smpl_skin_kernel(const float *__restrict_
       o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
       o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
     }
+  }
+}
+
+// Skinning only: verts = (sum_k w_k A_k) [v_posed;1] with v_posed already blended (tensor-core GEMM).  HBM-bound:
+// reads v_posed, writes verts.  CTA = 128 vertices x PT poses; A of the PT poses in smem.
+template <int PT, int NNZ>
+__global__ void __launch_bounds__(128) smpl_lbs_kernel(const float *__restrict__ v_posed, long long vp_ld,
+                                                       const int *__restrict__ lbs_idx, const float *__restrict__ lbs_w,
+                                                       int nnz_rt, const float *__restrict__ A12, float *__restrict__ verts,
+                                                       int N, int V, int out_mul, int out_off) {
+  __shared__ __align__(16) float As[PT * 288];
+  const int p0 = blockIdx.x * PT;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < PT * 288; i += 128) As[i] = (p0 + i / 288 < N) ? __ldg(A12 + (size_t)p0 * 288 + i) : 0.f;
+  __syncthreads();
+  const int v = blockIdx.y * 128 + tid;
+  if (v >= V) return;
+  const int nnz = NNZ > 0 ? NNZ : nnz_rt;
+  int jid[NNZ > 0 ? NNZ : 1];
+  float jw[NNZ > 0 ? NNZ : 1];
+  if (NNZ > 0) {
+#pragma unroll
+    for (int e = 0; e < NNZ; ++e) { jid[e] = __ldg(lbs_idx + (size_t)v * NNZ + e) * 12; jw[e] = __ldg(lbs_w + (size_t)v * NNZ + e); }
+  }
+#pragma unroll 4
+  for (int p = 0; p < PT; ++p) {
+    const int n = p0 + p;
+    if (n >= N) break;
+    const float *vp = v_posed + (size_t)n * vp_ld + (size_t)v * 3;
+    const float x = __ldg(vp), y = __ldg(vp + 1), z = __ldg(vp + 2);
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = 0.f;
+    const float *Ap = As + p * 288;
+    for (int e = 0; e < nnz; ++e) {
+      const int jj = NNZ > 0 ? jid[e < (NNZ > 0 ? NNZ : 1) ? e : 0] : __ldg(lbs_idx + (size_t)v * nnz + e) * 12;
+      const float w = NNZ > 0 ? jw[e < (NNZ > 0 ? NNZ : 1) ? e : 0] : __ldg(lbs_w + (size_t)v * nnz + e);
+      const float4 *a = reinterpret_cast<const float4 *>(Ap + jj);
+      const float4 a0 = a[0], a1 = a[1], a2 = a[2];
+      T[0] += w * a0.x; T[1] += w * a0.y; T[2] += w * a0.z; T[3] += w * a0.w;
+      T[4] += w * a1.x; T[5] += w * a1.y; T[6] += w * a1.z; T[7] += w * a1.w;
+      T[8] += w * a2.x; T[9] += w * a2.y; T[10] += w * a2.z; T[11] += w * a2.w;
+    }
+    float *o = verts + (((size_t)n * out_mul + out_off) * V + v) * 3;
+    o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+    o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+    o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
   }
 }
 
@@ -365,7 +424,7 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   float *A12 = reinterpret_cast<float *>(ws);
   float *Rs_w = A12 + (size_t)N * 288;
-  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off);
+  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off, nullptr, 0);
   int rc = hd::check_launch("smpl_pose_kernel");
   if (rc) return rc;
   const bool big = N >= 32 * 148;
@@ -377,6 +436,45 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
     rc = hd::check_launch("smpl_joints_kernel");
   }
   return rc;
+}
+
+// ---- staged SMPL (tensor-core blend): pose -> [hd_conv_gemm: v_posed = coef . dirs + v_template] -> lbs -> joints ----
+int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
+                 float *Jtr, float *A12, float *coef, int coef_ld, int out_mul, int out_off, void *ws, size_t ws_bytes,
+                 void *stream) {
+  HD_REQUIRE(c && beta && theta && A12 && ws && N > 0 && beta_ld >= 10 && theta_ld >= 72 && out_mul >= 1 && out_off >= 0 &&
+                 out_off < out_mul && (!coef || coef_ld >= 217),
+             "hd_smpl_pose: bad arguments");
+  if (ws_bytes < (size_t)N * 216 * sizeof(float)) return HD_ERR_WORKSPACE;
+  Tree tree;
+  if (!build_tree(c->parents, tree)) { hd::set_last_error_text("hd_smpl_pose: parents must satisfy parent[i] < i"); return HD_ERR_INVALID; }
+  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template,
+                                                                          c->J_shapedirs, reinterpret_cast<float *>(ws), Rs, Jtr,
+                                                                          A12, N, out_mul, out_off, coef, coef_ld);
+  return hd::check_launch("smpl_pose_kernel");
+}
+
+int hd_smpl_lbs(const hd_smpl_consts *c, const float *v_posed, long long vp_ld, const float *A12, float *verts, int N, int out_mul,
+                int out_off, void *stream) {
+  HD_REQUIRE(c && v_posed && A12 && verts && N > 0 && vp_ld >= (long long)c->num_verts * 3 && out_mul >= 1 && out_off >= 0 &&
+                 out_off < out_mul,
+             "hd_smpl_lbs: bad arguments");
+  dim3 grid(hd::ceil_div(N, 16), hd::ceil_div(c->num_verts, 128));
+  if (c->lbs_nnz == 4)
+    smpl_lbs_kernel<16, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(v_posed, vp_ld, c->lbs_idx, c->lbs_w, 4, A12, verts, N, c->num_verts, out_mul, out_off);
+  else
+    smpl_lbs_kernel<16, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(v_posed, vp_ld, c->lbs_idx, c->lbs_w, c->lbs_nnz, A12, verts, N, c->num_verts, out_mul, out_off);
+  return hd::check_launch("smpl_lbs_kernel");
+}
+
+int hd_smpl_joints(const hd_smpl_consts *c, const float *verts, const float *cam, int cam_ld, float *joints, float *kps, int N,
+                   int out_mul, int out_off, void *stream) {
+  HD_REQUIRE(c && verts && N > 0 && (joints || kps) && (!kps || (cam && cam_ld >= 3)) && out_mul >= 1 && out_off >= 0 && out_off < out_mul,
+             "hd_smpl_joints: bad arguments");
+  if (c->num_kps == 0) return HD_OK;
+  smpl_joints_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(verts, c->kp_ptr, c->kp_vidx, c->kp_w, cam, cam_ld, joints, kps, c->num_verts,
+                                                         c->num_kps, out_mul, out_off);
+  return hd::check_launch("smpl_joints_kernel");
 }
 
 int hd_rodrigues(const float *theta, float *R, int M, void *stream) {

@@ -465,7 +465,7 @@ class PackedIEFHead(object):
         self.fc1_phi = PackedConv(W1[:feat], device, post_shift=w[q + '/fc1/biases'], tc=tc)
         self.fc1_theta = PackedConv(W1[feat:], device, post_relu=True)
         self.fc2 = PackedConv(w[q + '/fc2/weights'], device, post_shift=w[q + '/fc2/biases'], post_relu=True, tc=tc)
-        self.fc3 = PackedConv(w[q + '/fc3/weights'], device, post_shift=w[q + '/fc3/biases'])
+        self.fc3 = PackedConv(w[q + '/fc3/weights'], device, post_shift=w[q + '/fc3/biases'], tc=tc)   # ragged N: scalar epilogue path
 
 
 class PackedIEF(object):
@@ -510,7 +510,7 @@ class IEFPlan(object):
             prev_ld = start_view.stride(0) if s == 0 else ld
             ops.append(head.fc1_theta.bind(prev, N, 1, 1, self.h1, in_ld=prev_ld, res=self.P, res_geom=(1024, 1, 1, 1), impl='simt'))
             ops.append(head.fc2.bind(self.h1, N, 1, 1, self.h2, impl=self.impl))
-            ops.append(head.fc3.bind(self.h2, N, 1, 1, state_view, out_ld=ld, res=prev, res_geom=(prev_ld, 1, 1, 1), impl='simt'))
+            ops.append(head.fc3.bind(self.h2, N, 1, 1, state_view, out_ld=ld, res=prev, res_geom=(prev_ld, 1, 1, 1), impl=self.impl))
         return ops
 
     def _bind(self, phi, theta0):
@@ -560,5 +560,5 @@ def run_ief_head(head: PackedIEFHead, phi, start, num_stage=3, impl='auto', stre
         pld = prev.stride(0)
         head.fc1_theta.bind(prev, N, 1, 1, h1, in_ld=pld, res=P, res_geom=(1024, 1, 1, 1), impl='simt').run(st)
         head.fc2.bind(h1, N, 1, 1, h2, impl=impl).run(st)
-        head.fc3.bind(h2, N, 1, 1, theta, out_ld=ld, res=prev, res_geom=(pld, 1, 1, 1), impl='simt').run(st)
+        head.fc3.bind(h2, N, 1, 1, theta, out_ld=ld, res=prev, res_geom=(pld, 1, 1, 1), impl=impl).run(st)
     return theta

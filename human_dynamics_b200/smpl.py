@@ -30,7 +30,7 @@ def load_smpl_model(pkl_path_or_dict):
 class SMPLConstants(object):
     """Device-resident SMPL constants in the layout the kernels want (hd_smpl_consts)."""
 
-    def __init__(self, model, joint_type='cocoplus', device=None):
+    def __init__(self, model, joint_type='cocoplus', device=None, tc=True):
         if joint_type not in ('cocoplus', 'lsp'):
             raise ValueError('BAD!! Unknown joint type: %s, it must be either "cocoplus" or "lsp"' % joint_type)
         dd = load_smpl_model(model)
@@ -116,6 +116,19 @@ class SMPLConstants(object):
             c.parents[i] = int(parents[i])
         self.c = c
         self._ws = None
+        # Tensor-core blend for large batches: v_posed = [beta | R-I] . dirs + v_template as one [N,256] x [256, V*3] GEMM
+        # (fp16 head/remainder split, FP32-class), then HBM-shaped skinning.  Small batches use the fused SIMT kernel.
+        self.tc_min_batch = 256
+        self.blend = None
+        self._tc_bufs = {}
+        if tc:
+            from .nets import PackedConv
+            self.vp_ld = (V * 3 + 3) // 4 * 4
+            wb = np.zeros((256, self.vp_ld), np.float32)
+            wb[:217, :V * 3] = dirs
+            bias = np.zeros(self.vp_ld, np.float32)
+            bias[:V * 3] = v_template.reshape(-1)
+            self.blend = PackedConv(wb, dev, post_shift=bias, tc='tc3h')
 
     def workspace(self, N):
         need = int(lib.hd_smpl_workspace_bytes(N))
@@ -149,7 +162,9 @@ class SMPLConstants(object):
         kps = None
         if cam is not None:
             kps = o.get('kps') if 'kps' in o else torch.empty((N * mul, K, 2), dtype=torch.float32, device=dev)
-        if N > 0:
+        if N >= self.tc_min_batch and self.blend is not None and self.blend.tc:
+            self._forward_tc(beta, theta, cam, N, verts, joints, Rs, Jtr, kps, int(mul), int(off))
+        elif N > 0:
             ws = self.workspace(N)
             rc = lib.hd_smpl_forward(C.byref(self.c), fptr(beta), beta.stride(0), fptr(theta), theta.stride(0), N,
                                      fptr(verts), fptr(joints), fptr(Rs), fptr(Jtr),
@@ -158,6 +173,32 @@ class SMPLConstants(object):
                                      dptr(ws), ws.numel(), current_stream())
             check(rc, 'hd_smpl_forward')
         return {'verts': verts, 'joints': joints, 'Rs': Rs, 'Jtr': Jtr, 'kps': kps}
+
+    def _forward_tc(self, beta, theta, cam, N, verts, joints, Rs, Jtr, kps, mul, off):
+        """pose -> tensor-core blend GEMM -> skinning -> keypoints (hd_smpl_pose / hd_conv_gemm / hd_smpl_lbs / hd_smpl_joints)."""
+        dev = beta.device
+        if N not in self._tc_bufs:
+            f32 = dict(dtype=torch.float32, device=dev)
+            coef = torch.empty((N, 256), **f32)
+            vpos = torch.empty((N, self.vp_ld), **f32)
+            a12 = torch.empty((N, 288), **f32)
+            rsw = torch.empty((N, 216), **f32)
+            op = self.blend.bind(coef, N, 1, 1, vpos, impl='tc3h')
+            self._tc_bufs[N] = (coef, vpos, a12, rsw, op)
+        coef, vpos, a12, rsw, op = self._tc_bufs[N]
+        st = current_stream()
+        check(lib.hd_smpl_pose(C.byref(self.c), fptr(beta), beta.stride(0), fptr(theta), theta.stride(0), N, fptr(Rs), fptr(Jtr),
+                               fptr(a12), fptr(coef), 256, mul, off, dptr(rsw), rsw.numel() * 4, st), 'hd_smpl_pose')
+        op.run(st)
+        check(lib.hd_smpl_lbs(C.byref(self.c), fptr(vpos), self.vp_ld, fptr(a12), fptr(verts), N, mul, off, st), 'hd_smpl_lbs')
+        if (joints is not None or kps is not None) and self.num_kps > 0:
+            check(lib.hd_smpl_joints(C.byref(self.c), fptr(verts), fptr(cam) if cam is not None else None,
+                                     cam.stride(0) if cam is not None else 0, fptr(joints), fptr(kps) if kps is not None else None,
+                                     N, mul, off, st), 'hd_smpl_joints')
+
+
+def _noop():
+    pass
 
 
 def batch_rodrigues(theta):

@@ -137,6 +137,18 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
                     float *verts, float *joints, float *Rs, float *Jtr,
                     const float *cam, int cam_ld, float *kps, int out_mul, int out_off,
                     void *ws, size_t ws_bytes, void *stream);
+/* Staged form of the same computation for large batches: the dense shape/pose blend (batch_smpl.py:110-112,127-133) is one
+ * [N,256] x [256, V*3] GEMM on the tensor cores (hd_conv_gemm over `coef` with the packed `dirs`, bias = v_template), so the
+ * rest is HBM-shaped:  hd_smpl_pose (Rodrigues + FK; also writes the GEMM operand rows coef[n] = [beta | R-I | 0]) ->
+ * hd_conv_gemm -> hd_smpl_lbs (skinning of the blended v_posed [N, vp_ld]) -> hd_smpl_joints (keypoints + projection).
+ * ws of hd_smpl_pose: N*216 floats. */
+int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
+                 float *Jtr, float *A12, float *coef, int coef_ld, int out_mul, int out_off, void *ws, size_t ws_bytes,
+                 void *stream);
+int hd_smpl_lbs(const hd_smpl_consts *c, const float *v_posed, long long vp_ld, const float *A12, float *verts, int N, int out_mul,
+                int out_off, void *stream);
+int hd_smpl_joints(const hd_smpl_consts *c, const float *verts, const float *cam, int cam_ld, float *joints, float *kps, int N,
+                   int out_mul, int out_off, void *stream);
 /* batch_rodrigues: theta [M,3] -> R [M,3,3]. */
 int hd_rodrigues(const float *theta, float *R, int M, void *stream);
 /* batch_global_rigid_transformation: Rs [N,24,3,3], Js [N,24,3], parents host int[24] -> new_J [N,24,3], A [N,24,4,4]. */

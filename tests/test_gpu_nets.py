@@ -115,6 +115,49 @@ def test_conv_gemm_tcgen05_3xf16(case):
     assert err < 5e-5, err
 
 
+@pytest.mark.parametrize('shape', [
+    # n, H, Cin, Cout, k, stride, with_res, fp32_out
+    (3, 14, 64, 256, 1, 1, True, True),      # DUAL variant (K <= 256): conv3-style, residual + fp32 + split outputs
+    (2, 28, 128, 64, 3, 1, False, False),    # 3x3, split output only, BN=64 tile
+    (2, 14, 256, 128, 3, 2, False, False),   # strided 3x3 through the cp.async gather (zero-fill padding)
+    (5, 7, 512, 2048, 1, 1, True, True),     # non-DUAL, many N tiles, ragged M (245 rows)
+])
+def test_conv_gemm_presplit_activations(shape):
+    """A operand as a pre-activated fp16 head/remainder pair (cp.async producer) and the epilogue's second output
+    relu(v*s2+b2) as such a pair, against an fp64 reference of the same arithmetic."""
+    from human_dynamics_b200 import _lib
+    from human_dynamics_b200.nets import PackedConv
+    n, H, Cin, Cout, k, stride, with_res, fp32_out = shape
+    rng = np.random.RandomState(sum(shape))
+    dev = torch.device('cuda')
+    x = np.maximum(rng.normal(0, 1, size=(n, H, H, Cin)), 0).astype(np.float32)          # already pre-activated
+    w = (rng.normal(0, 1, size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    bias = rng.normal(0, 0.2, size=Cout).astype(np.float32)
+    s2 = rng.uniform(0.5, 1.5, size=Cout).astype(np.float32); b2 = rng.normal(0, 0.3, size=Cout).astype(np.float32)
+    pc = PackedConv(w, dev, post_shift=bias, stride=stride, pad=(k // 2, k // 2), tc='tc3h')
+    xt = torch.from_numpy(x).to(dev)
+    hi = xt.half(); lo = ((xt - hi.float()) * 2048).half()
+    Ho = (H + 2 * (k // 2) - k) // stride + 1
+    out = torch.zeros((n, Ho, Ho, Cout), device=dev) if fp32_out else None
+    oh = torch.zeros((n, Ho, Ho, Cout), dtype=torch.float16, device=dev); ol = torch.zeros_like(oh)
+    r = rng.normal(0, 1, size=(n, Ho, Ho, Cout)).astype(np.float32) if with_res else None
+    rt = torch.from_numpy(r).to(dev) if with_res else None
+    op = pc.bind(None, n, H, H, out, inp_split=(hi, lo), out_split=(oh, ol), res=rt,
+                 post2=(torch.from_numpy(s2).to(dev), torch.from_numpy(b2).to(dev), 1), impl='tc3h')
+    assert op.d.impl == _lib.HD_IMPL_TC_3XF16
+    op.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ac = F.pad(torch.from_numpy(x).double().permute(0, 3, 1, 2), (k // 2,) * 4)
+    v = F.conv2d(ac, torch.from_numpy(w).double().permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1) + torch.from_numpy(bias).double()
+    if with_res:
+        v = v + torch.from_numpy(r).double()
+    y = torch.relu(v * torch.from_numpy(s2).double() + torch.from_numpy(b2).double())
+    if fp32_out:
+        assert rel_err(out.cpu().numpy(), v.numpy()) < 2e-5
+    got = oh.float().cpu().double() + ol.float().cpu().double() / 2048.0       # the pair represents y to ~2^-22
+    assert rel_err(got.numpy(), y.numpy()) < 2e-5
+
+
 def test_conv_gemm_tcgen05_1xtf32_is_tf32_accurate():
     rng = np.random.RandomState(3)
     err, _ = _conv_case(rng, 4, 28, 28, 128, 128, 3, 3, 1, (1, 1), None, None, True, True, impl='tc1')

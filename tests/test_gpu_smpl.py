@@ -13,9 +13,9 @@ def rel_err(a, b):
     return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
 
 
-def _run(model, beta, theta, cam=None, joint_type='cocoplus'):
+def _run(model, beta, theta, cam=None, joint_type='cocoplus', tc=True):
     from human_dynamics_b200.smpl import SMPLConstants
-    c = SMPLConstants(model, joint_type=joint_type)
+    c = SMPLConstants(model, joint_type=joint_type, tc=tc)
     o = c.forward(torch.from_numpy(beta).cuda(), torch.from_numpy(theta).cuda(),
                   cam=None if cam is None else torch.from_numpy(cam).cuda())
     torch.cuda.synchronize()
@@ -45,6 +45,22 @@ def test_smpl_forward_matches_oracle(smpl_model, n, zero_pose):
         assert rel_err(got[k], ref[k]) < REL, k
     if zero_pose:       # C1: theta = 0 => Rs = I exactly, verts = v_shaped
         assert np.array_equal(got['Rs'], np.tile(np.eye(3, dtype=np.float32), (n, 24, 1, 1)))
+
+
+@pytest.mark.parametrize('n', [256, 777])
+def test_smpl_tensor_core_blend_path(smpl_model, smpl_model_dense, n):
+    """N >= 256 takes the staged path (pose -> tcgen05 blend GEMM -> skinning -> keypoints); must agree with the oracle
+    and, to rounding, with the fused FP32 kernel."""
+    from human_dynamics_b200 import synthetic
+    for model, jt in ((smpl_model, 'cocoplus'), (smpl_model_dense, 'lsp')):
+        beta, theta = synthetic.make_smpl_inputs(n, seed=n)
+        cam = np.random.RandomState(n).uniform(0.5, 1.5, size=(n, 3)).astype(np.float32)
+        got = _run(model, beta, theta, cam, joint_type=jt)
+        ref = _oracle(model, beta, theta, cam, joint_type=jt)
+        fused = _run(model, beta, theta, cam, joint_type=jt, tc=False)
+        for k in ('verts', 'joints', 'Rs', 'Jtr', 'kps'):
+            assert rel_err(got[k], ref[k]) < REL, k
+            assert rel_err(got[k], fused[k]) < 2e-5, k
 
 
 def test_smpl_dense_weights_lsp(smpl_model_dense):
