@@ -184,19 +184,6 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (GATHER) {      // k = (ky*KW + kx)*Cin + ci  ->  ky<<24 | kx<<16 | (kx*Cin + ci); 0xFFFFFFFF beyond K
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + C::LUT_OFFSET);
-    for (int k = threadIdx.x; k < 256; k += NUM_THREADS) {
-      uint32_t e = 0xFFFFFFFFu;
-      if (k < p.K) {
-        const int tap = k / p.Cin, ci = k - tap * p.Cin;
-        const int ky = tap / p.KW, kx = tap - ky * p.KW;
-        e = ((uint32_t)ky << 24) | ((uint32_t)kx << 16) | (uint32_t)(kx * p.Cin + ci);
-      }
-      lut[k] = e;
-    }
-    __syncthreads();
-  }
   const uint32_t tmem_d = *tmem_slot;
   const int xmode = p.dbg ? (int)p.dbg[15] : 0;      // timing experiments (hd_conv_gemm_profile only; results invalid)
   // TMEM columns: [0,BN) cross terms 0, [BN,2BN) cross terms 1, [2BN,3BN) main 0, [3BN,4BN) main 1
@@ -272,25 +259,30 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     int pf_kc = 0, pf_ti = 0;              // next chunk to prefetch
     auto prefetch = [&](float4 *dst, uint32_t &vm) {
       if (pf_kc == 0) enter_tile(pf_ti, pf_rs);
-      if (GATHER) {          // element-wise gather through the k -> (ky, kx, offset) table (L1-resident input rows)
-        const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + C::LUT_OFFSET) + pf_kc * BKE + j * (4 * V);
-        uint32_t ent[4 * V];
-#pragma unroll
-        for (int e = 0; e < 4 * V; ++e) ent[e] = lut[e];
+      if (GATHER) {
+        // Ragged Cin (conv1, 7x7x3): K is laid out ky-major with each kernel row's KW*Cin contiguous input floats padded to a
+        // multiple of 8 (21 -> 24), so a thread's 8 consecutive k belong to ONE kernel row and are 8 consecutive floats in
+        // memory: one address per (row, chunk), element-wise bounds only for the left/right image edge.
+        const int seg = p.KW * p.Cin, segp = (seg + 7) & ~7;
+        const int g8 = (pf_kc * BKE + j * (4 * V)) / 8;          // 8-float group index along the padded K
+        const int gpr = segp >> 3;                               // groups per kernel row
+        const int ky = g8 / gpr, r0 = (g8 - ky * gpr) * 8;
         vm = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float xs[4 * V];
-          const float *rowp = p.in + ((size_t)(pf_rs.n[i] < 0 ? 0 : pf_rs.n[i]) * p.H * p.W) * p.in_ld;
+          const int iy = pf_rs.iy[i] + ky;
+          const bool okr = pf_rs.n[i] >= 0 && ky < p.KH && iy >= 0 && iy < p.H;
+          const int c0 = pf_rs.ix[i] * p.Cin + r0;               // float offset inside the input row (may be < 0 at the left edge)
+          const float *src = p.in + ((size_t)((size_t)(okr ? pf_rs.n[i] : 0) * p.H + (okr ? iy : 0)) * p.W) * p.in_ld + c0;
+          const int rowlen = p.W * p.Cin;
+          float xs[8];
 #pragma unroll
-          for (int e = 0; e < 4 * V; ++e) {
-            const int ky = (int)(ent[e] >> 24), kx = (int)((ent[e] >> 16) & 0xFF), off = (int)(ent[e] & 0xFFFF);
-            const int iy = pf_rs.iy[i] + ky, ix = pf_rs.ix[i] + kx;
-            const bool ok = ent[e] != 0xFFFFFFFFu && pf_rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-            xs[e] = ok ? __ldg(rowp + ((long long)iy * p.W + pf_rs.ix[i]) * p.in_ld + off) : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            const bool ok = okr && (r0 + e) < seg && (c0 + e) >= 0 && (c0 + e) < rowlen;
+            xs[e] = ok ? __ldg(src + e) : 0.f;
           }
-#pragma unroll
-          for (int v = 0; v < V; ++v) dst[i * V + v] = make_float4(xs[4 * v], xs[4 * v + 1], xs[4 * v + 2], xs[4 * v + 3]);
+          dst[i * V] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+          dst[i * V + V - 1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
           if (pf_rs.n[i] >= 0) vm |= 1u << i;
         }
         if (++pf_kc == num_k) { pf_kc = 0; ++pf_ti; }
@@ -741,9 +733,9 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
     return p.Cout <= 64 ? launch_tc<64, true, 2, true, false, true>(p, d, st) : launch_tc<128, true, 2, true, false, true>(p, d, st);
   }
   if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded
-    if (p.K_pad % 64 != 0 || p.K_pad < p.K || p.K_pad > 256 || p.Cout > 64 || p.pre_scale || p.KW > 255 || p.KH > 255 ||
-        p.KW * p.Cin > 65535) {
-      set_last_error_text("hd_conv_gemm(tc gather): needs K_pad % 64 == 0, K <= K_pad <= 256, Cout <= 64, no prologue");
+    const int segp = (p.KW * p.Cin + 7) & ~7;
+    if (p.K_pad % 64 != 0 || p.K_pad < p.KH * segp || p.Cout > 64 || p.pre_scale || p.in_ld != p.Cin) {
+      set_last_error_text("hd_conv_gemm(tc gather): needs K_pad % 64 == 0, K_pad >= KH*roundup8(KW*Cin), Cout <= 64, dense pixels, no prologue");
       return HD_ERR_INVALID;
     }
     return launch_tc<64, true, 2, true, true>(p, d, st);

@@ -79,16 +79,23 @@ class PackedConv(object):
         self.tc = False            # False | 'f16' | 'tf32': which tensor-core packing this layer carries
         self.K_pad = 0
         want = {True: 'f16', 'auto': 'f16', 'tc3h': 'f16', 'tc3': 'tf32', 'tc1': 'tf32'}.get(tc, tc)
-        gather = want == 'f16' and self.Cin % 32 != 0 and self.K <= 256 and self.Cout <= 64   # conv1: element-wise gather
+        gather = want == 'f16' and self.Cin % 32 != 0 and self.Cout <= 64   # conv1: row-segment gather producer
         if want == 'f16' and self.Cin % 64 != 0 and not gather:
             want = 'tf32'
         self.gather = bool(gather)
         if want in ('f16', 'tf32') and (self.Cin % 32 == 0 or gather):
-            self.K_pad = (self.K + 63) // 64 * 64 if gather else self.K
+            seg = self.KW * self.Cin
+            segp = (seg + 7) // 8 * 8                        # gather layout: each kernel row's KW*Cin floats padded to x8
+            self.K_pad = (self.KH * segp + 63) // 64 * 64 if gather else self.K
             box = 64 if self.Cout <= 64 else 128              # must equal the kernel's N tile (conv_tc.cu)
             rows = (self.Cout + box - 1) // box * box
             w_nk = np.zeros((rows, self.K_pad), np.float32)
-            w_nk[:self.Cout, :self.K] = w_kn.T
+            if gather:                                       # K index = ky*segp + (kx*Cin + ci)   (conv_tc.cu GATHER producer)
+                wg = w_hwio.reshape(self.KH, seg, self.Cout)
+                for ky in range(self.KH):
+                    w_nk[:self.Cout, ky * segp:ky * segp + seg] = wg[ky].T
+            else:
+                w_nk[:self.Cout, :self.K] = w_kn.T
             if want == 'f16':
                 hi, lo = f16_split(w_nk)
                 self.w_nk_hi = torch.from_numpy(hi).to(device)
