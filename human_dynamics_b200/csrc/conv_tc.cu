@@ -100,6 +100,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Nearest value with the low 13 mantissa bits clear (all the tf32 datapath reads).
 __device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -125,7 +135,8 @@ struct Cfg {
   static constexpr int SLAB = 32;                               // accumulator columns transposed per epilogue pass
   static constexpr int STG_LD = SLAB + 4;                       // padded row of the per-warp 32 x 32 staging tile (floats)
   static constexpr int STG_OFFSET = BAR_OFFSET + 128;
-  static constexpr int STG_BYTES = DW * 32 * STG_LD * 4;        // one 32 x 32 tile per drain warp
+  static constexpr int NSTG = DUAL ? 2 : 1;                     // DUAL has the smem for double-buffered residual slabs
+  static constexpr int STG_BYTES = DW * NSTG * 32 * STG_LD * 4; // 32 x 32 tile(s) per drain warp
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
   static constexpr int SMEM_BYTES = LUT_OFFSET + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
@@ -190,7 +201,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 
   if (warp >= DW && warp < DW + 8) {
     // =============================== A producers (256 threads) ===============================
-    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int t = threadIdx.x - DW * 32;  // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
@@ -391,12 +402,12 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   } else if (warp < DW) {
     // =============================== drain + epilogue ===============================
     const int dgroup = warp >> 2, quarter = warp & 3;     // DUAL: group 0 takes even tiles, group 1 odd tiles
-    if (DUAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    if (DUAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
-    float *stg = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (32 * C::STG_LD);
+    float *stg0 = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::NSTG * 32 * C::STG_LD);
     const int hw = p.Ho * p.Wo;
     for (int ti = dgroup; ti < my_tiles; ti += (DUAL ? 2 : 1)) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -404,18 +415,24 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       float sums[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) sums[i] = 0.f;
-      if (p.res && p.vec_out) {       // pull this tile's residual rows towards L2 while the main loop runs
-        const int m = m0 + quarter * 32 + lane;
-        if (m < p.M) {
-          size_t rrow = (size_t)m;
-          if (!(p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo)) {
-            const int n = m / hw;
-            const int rr = m - n * hw;
-            const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-            rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+      if (p.res && p.vec_out) {       // pull the residual rows of this group's NEXT tile towards L2 (a whole tile period of lead
+                                      // time; the very first tile is prefetched on entry), so the epilogue's cp.asyncs hit L2
+        const int tstep = DUAL ? 2 : 1;
+        const int tin = (ti == dgroup) ? ti : ti + tstep;                 // first iteration: this tile
+        for (int tn = tin; tn <= ti + tstep && tn < my_tiles; tn += tstep) {
+          const int tilen = (int)blockIdx.x + tn * (int)gridDim.x;
+          const int m = (tilen / tiles_n) * BM + quarter * 32 + lane, n0n = (tilen % tiles_n) * BN;
+          if (m < p.M) {
+            size_t rrow = (size_t)m;
+            if (!(p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo)) {
+              const int n = m / hw;
+              const int rr = m - n * hw;
+              const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+              rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+            }
+            const float *rp = p.res + rrow * p.res_ld + n0n;
+            for (int c = 0; c < BN && n0n + c < p.Cout; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
           }
-          const float *rp = p.res + rrow * p.res_ld + n0;
-          for (int c = 0; c < BN && n0 + c < p.Cout; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
         }
       }
       for (int g = 0; g < num_g; ++g) {
@@ -426,11 +443,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         if (prof) t_wait += clock64() - tw0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * (2 + b) + c0), v);
+        for (int c0 = 0; c0 < BN; c0 += 16) {       // x16 loads: 16 live temporaries next to the BN running sums
+          uint32_t v[16];
+          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * (2 + b) + c0), v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
+          for (int i = 0; i < 16; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -439,11 +456,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       if (SPLIT) {      // the tile's last accf commit also covers every cross-term MMA of the tile
         const int sb = ti & 1;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_d + lane_off + (uint32_t)(BN * sb + c0), v);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * sb + c0), v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sums[c0 + i] += __uint_as_float(v[i]) * (HALF ? (1.0f / 2048.0f) : 1.0f);
+          for (int i = 0; i < 16; ++i) sums[c0 + i] += __uint_as_float(v[i]) * (HALF ? (1.0f / 2048.0f) : 1.0f);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -459,40 +476,55 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       const int rq = lane >> 3, c4 = (lane & 7) * 4;       // coalesced phase: row rq + 4*i of the warp's 32, columns c4..c4+3 of the slab
       const bool res_plain = p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo;
       const bool res_smem = p.res != nullptr && p.vec_out;
-#pragma unroll
-      for (int sl = 0; sl < BN / C::SLAB; ++sl) {
+      const int mrow0 = m0 + quarter * 32 + rq;             // this lane's first row of a slab; its rows are mrow0 + 4*i
+      // residual slab `sl` -> staging buffer `buf` (cp.async, zero-fill outside the tensor); one commit group per slab
+      auto fetch_res = [&](int sl, float *buf) {
         const int co = n0 + sl * C::SLAB + c4;
         const bool cvalid = co < p.Cout;
-        __syncwarp();
-        const int mrow0 = m0 + quarter * 32 + rq;           // this lane's first row of the slab; its rows are mrow0 + 4*i
-        if (res_smem) {
-          const uint32_t tdst = smem_u32(stg + rq * C::STG_LD + c4);
-          if (res_plain) {                                    // residual row == output row: step a pointer, no index math
-            const float *rp = p.res + (size_t)mrow0 * p.res_ld + (cvalid ? co : 0);
-            const size_t rstep = 4 * (size_t)p.res_ld;
+        const uint32_t tdst = smem_u32(buf + rq * C::STG_LD + c4);
+        if (res_plain) {                                      // residual row == output row: step a pointer, no index math
+          const float *rp = p.res + (size_t)mrow0 * p.res_ld + (cvalid ? co : 0);
+          const size_t rstep = 4 * (size_t)p.res_ld;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool ok = cvalid && (mrow0 + 4 * i) < p.M;
-              cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), ok ? (const void *)(rp + i * rstep) : (const void *)p.res,
-                         (ok && !(xmode & 16)) ? 16u : 0u);
-            }
-          } else {
-#pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-              const int m = mrow0 + 4 * i;
-              const bool ok = m < p.M && cvalid;
-              size_t rrow = 0;
-              if (ok) {
-                const int n = m / hw;
-                const int rr = m - n * hw;
-                const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-                rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
-              }
-              cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), p.res + rrow * p.res_ld + (ok ? co : 0), (ok && !(xmode & 16)) ? 16u : 0u);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = cvalid && (mrow0 + 4 * i) < p.M;
+            cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), ok ? (const void *)(rp + i * rstep) : (const void *)p.res,
+                       (ok && !(xmode & 16)) ? 16u : 0u);
           }
-          cp_async_commit();
-          cp_async_wait<0>();
+        } else {
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const bool ok = m < p.M && cvalid;
+            size_t rrow = 0;
+            if (ok) {
+              const int n = m / hw;
+              const int rr = m - n * hw;
+              const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+              rrow = ((size_t)n * p.res_H + (size_t)oy * p.res_stride) * p.res_W + (size_t)ox * p.res_stride;
+            }
+            cp_async16(tdst + (uint32_t)(i * 4 * C::STG_LD * 4), p.res + rrow * p.res_ld + (ok ? co : 0), (ok && !(xmode & 16)) ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+      };
+      constexpr int NSL = BN / C::SLAB;
+      __syncwarp();
+      if (res_smem && C::NSTG == 2) fetch_res(0, stg0);       // double-buffered: slab sl+1 is in flight while slab sl is processed
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int co = n0 + sl * C::SLAB + c4;
+        const bool cvalid = co < p.Cout;
+        float *stg = stg0 + (C::NSTG == 2 ? (sl & 1) * (32 * C::STG_LD) : 0);
+        __syncwarp();
+        if (res_smem) {
+          if (C::NSTG == 2) {
+            if (sl + 1 < NSL) { fetch_res(sl + 1, stg0 + ((sl + 1) & 1) * (32 * C::STG_LD)); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+          } else {
+            fetch_res(sl, stg);
+            cp_async_wait<0>();
+          }
           __syncwarp();
         }
         float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -576,7 +608,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     if (prof) { p.dbg[2] = clock64() - t_start; p.dbg[3] = t_wait; p.dbg[4] = t_epi; }
   } else {
     // register pool = threads x launch allocation (512 x 128, or 640 x 96 for DUAL); the budgets below must fit in it or
-    // setmaxnreg.inc never returns:  4-warp: 128*200 + 256*136 + 128*40 = 65536;  DUAL: 256*168 + 256*56 + 128*24 = 60416 <= 61440
+    // setmaxnreg.inc never returns:  4-warp: 128*200 + 256*136 + 128*40 = 65536;  DUAL: 256*192 + 256*32 + 128*24 = 60416 <= 61440
     if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == W_TMA) {
