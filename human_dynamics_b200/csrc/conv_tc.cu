@@ -561,7 +561,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         const size_t ostep = 4 * (size_t)p.out_ld, hstep = 4 * (size_t)p.out2_ld;
         const bool st32 = op != nullptr && !(xmode & 8), st16 = ohp != nullptr && !(xmode & 32);
 #pragma unroll 4
-        for (int i = 0; i < 8; ++i) {      // 4 independent rows in flight per lane: this loop is latency-, not issue-bound
+        for (int i = 0; i < 8; ++i) {      // 4 independent rows in flight per lane (8 measured slower: code size); latency-, not issue-bound
           const int m = mrow0 + 4 * i;
           if (m >= p.M || !cvalid) continue;
           const float4 a = *reinterpret_cast<const float4 *>(tsrc + i * 4 * C::STG_LD);

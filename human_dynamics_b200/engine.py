@@ -76,6 +76,22 @@ class HMMREngine(object):
                 self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(cut, nu), root=False, tail=True)
         return self._resnet_plans[key]
 
+    H2D_PIECE = 32           # frames per host->device copy piece (one event each)
+
+    def stage_a_schedule(self, N, streaming):
+        """[(start, n)] of the stage-A passes.  When frames are still arriving from the host the first pass is kept small
+        (one copy piece) so compute starts after 19 MB instead of a full chunk; all other passes use `frame_chunk`."""
+        cA = max(1, min(int(self.config.frame_chunk), N))
+        out, i = [], 0
+        if streaming and N > cA and cA > self.H2D_PIECE:
+            out.append((0, self.H2D_PIECE))
+            i = self.H2D_PIECE
+        while i < N:
+            n = min(cA, N - i)
+            out.append((i, n))
+            i += n
+        return out
+
     def _trunk(self, images, phi, events=None):
         """ResNet over N frames in two stages: root + blocks 1-2 per `frame_chunk` frames (working set near L2),
         then blocks 3-4 + postnorm/mean per `late_chunk` frames (small maps need many frames to fill the SMs).
@@ -97,11 +113,11 @@ class HMMREngine(object):
                                    torch.empty(mid.shape, dtype=torch.float16, device=self.device))
             mid_split = self._phi[skey]
         main = torch.cuda.current_stream()
-        for ci, i in enumerate(range(0, N, cA)):
-            n = min(cA, N - i)
+        for i, n in self.stage_a_schedule(N, events is not None):
             plan = self._resnet_plan(n, size, 'A')
             if events is not None:
-                main.wait_event(events[ci])
+                for ev in events[i // self.H2D_PIECE:(i + n + self.H2D_PIECE - 1) // self.H2D_PIECE]:
+                    main.wait_event(ev)
             plan.set_output(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
             plan.run(images[i:i + n], None, st)
         for i in range(0, N, cB):
@@ -219,7 +235,7 @@ class HMMREngine(object):
             self._phi[('phi', N)] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
             self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
         dev_img, phi = self._phi[key], self._phi[('phi', N)]
-        chunk = max(1, min(int(self.config.frame_chunk), N))
+        chunk = self.H2D_PIECE
         starts = list(range(0, N, chunk))
         ekey = ('ev', len(starts))
         if ekey not in self._phi:
@@ -234,20 +250,34 @@ class HMMREngine(object):
                 dev_img[i:i + n].copy_(flat[i:i + n], non_blocking=True)
                 ev.record(cs)
         self._trunk(dev_img, phi, events)
-        out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
-        keys = [k for k in (fetch or self.FETCH_KEYS) if k in out]
-        host, d2h = {}, 0
-        for k in keys:
-            v = out[k]
-            hk = ('host', k, tuple(v.shape))
-            if hk not in self._phi:
-                self._phi[hk] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
-            self._phi[hk].copy_(v, non_blocking=True)
-            host[k] = self._phi[hk]
-            d2h += v.numel() * 4
+        want = list(fetch or self.FETCH_KEYS)
+        host, counted = {}, [0]
+
+        def to_host(tensors, stream):
+            for k, v in tensors.items():
+                if k not in want or k in host:
+                    continue
+                hk = ('host', k, tuple(v.shape))
+                if hk not in self._phi:
+                    self._phi[hk] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
+                with torch.cuda.stream(stream):
+                    self._phi[hk].copy_(v, non_blocking=True)
+                host[k] = self._phi[hk]
+                counted[0] += v.numel() * 4
+
+        def main_ready(main_out):            # dt=0 outputs: device->host on the copy stream, overlapped with the delta heads
+            ev = torch.cuda.Event()
+            ev.record(main)
+            cs.wait_event(ev)
+            to_host(main_out, cs)
+
+        out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame, on_main_ready=main_ready)
+        to_host({k: v for k, v in out.items() if not k.startswith('_')}, main)
+        main.wait_stream(cs)                  # one synchronisation point for the caller: the current stream
+        d2h = counted[0]
         return host, flat.numel() * 4, d2h
 
-    def predict_from_features(self, phi, single_frame=False):
+    def predict_from_features(self, phi, single_frame=False, on_main_ready=None):
         B, T = phi.shape[0], phi.shape[1]
         N = B * T
         if single_frame:
@@ -261,8 +291,10 @@ class HMMREngine(object):
                 strips = self.hallucinate(phi)
             else:
                 raise Exception('Pred mode {} not recognized'.format(mode))
-            omega, deltas = self.regress(strips.reshape(N, -1))
-        dts = sorted(deltas.keys())
+            plan = self._ief_plan(N, tuple(sorted(self.ief.deltas.keys())))
+            omega = plan.run_main(strips.reshape(N, -1), self.theta_mean(N))
+            deltas = None
+        dts = sorted(self.ief.deltas.keys()) if not single_frame else []
         D = len(dts)
         K, V = self.smpl.num_kps, self.smpl.num_verts
         o0, od = self._out_buffers(N, D)
@@ -272,6 +304,10 @@ class HMMREngine(object):
         out = {'cams': cams.reshape(B, T, 3), 'joints': o0['joints'].view(B, T, K, 3), 'kps': o0['kps'].view(B, T, K, 2),
                'poses': o0['Rs'].view(B, T, 24, 3, 3), 'shapes': omega[:, 75:85].reshape(B, T, 10),
                'verts': o0['verts'].view(B, T, V, 3), 'omegas': omega.view(B, T, 85)}
+        if on_main_ready is not None:        # the dt=0 results can start their trip to the host while the delta heads compute
+            on_main_ready(out)
+        if D:
+            deltas = self._ief_plan(N, tuple(dts)).run_deltas()
         if D:
             # ... and every delta instance; cams come from the dt=0 prediction (set_cams, tester.py:210-213).
             # Pose n of delta i is written to slot n*D+i, i.e. directly into the [B,T,D,...] stacking of tester.py:252.

@@ -528,19 +528,29 @@ class IEFPlan(object):
             self.delta_ops[dt] = self._head_ops(self.p.deltas[dt], phi, view, view, view.stride(0))
         self._bound_for = (phi.data_ptr(), theta0.data_ptr())
 
-    def run(self, phi, theta0, stream=None):
-        """phi (N,2048), theta0 (N,85) contiguous -> (theta (N,85), {dt: (N,85) view of delta_all[:, i]})."""
+    def run_main(self, phi, theta0, stream=None):
+        """Main 85-d head only: phi (N,2048), theta0 (N,85) contiguous -> theta (N,85)."""
         st = current_stream() if stream is None else stream
         if self._bound_for != (phi.data_ptr(), theta0.data_ptr()):
             self._bind(phi, theta0)
         for op in self.main_ops:
             op.run(st)
+        return self.theta
+
+    def run_deltas(self, stream=None):
+        """Delta heads, started from the main prediction (run_main must have run): {dt: (N,85) view of delta_all[:, i]}."""
+        st = current_stream() if stream is None else stream
         for dt in self.delta_keys:
             check(lib.hd_ief_delta_init(fptr(self.theta), fptr(self.delta_out[dt]), self.delta_out[dt].stride(0), self.N, st),
                   'hd_ief_delta_init')
             for op in self.delta_ops[dt]:
                 op.run(st)
-        return self.theta, self.delta_out
+        return self.delta_out
+
+    def run(self, phi, theta0, stream=None):
+        """phi (N,2048), theta0 (N,85) contiguous -> (theta (N,85), {dt: (N,85) view of delta_all[:, i]})."""
+        theta = self.run_main(phi, theta0, stream)
+        return theta, self.run_deltas(stream)
 
     @property
     def num_launches(self):
