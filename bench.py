@@ -153,7 +153,7 @@ def main():
     ap.add_argument('--mode', default=os.environ.get('HD_IMPL', 'auto'), choices=['auto', 'tc3h', 'tc3', 'simt', 'tc1'],
                     help='auto/tc3h = tcgen05 fp16 head+remainder split x3 (FP32-class parity mode, the headline); tc3 = 3xTF32 (also FP32-class); '
                          'tc1 = single-pass TF32 (fails parity); simt = exact FP32 CUDA cores')
-    ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '128')))
+    ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '160')))
     ap.add_argument('--late-chunk', type=int, default=int(os.environ.get('HD_LATE_CHUNK', '640')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -28,6 +28,6 @@ class HMMRConfig(object):
     weights: Any = None
     smpl_model: Any = None
     impl: str = os.environ.get('HD_IMPL', 'auto')   # 'auto' (= 'tc3h' where Cin % 64 == 0, else 'tc3', else 'simt') | 'tc3h' | 'tc3' | 'tc1' | 'simt'
-    frame_chunk: int = 128        # frames per pass of ResNet root + blocks 1-2 (activation working set vs. L2)
+    frame_chunk: int = 160        # frames per pass of ResNet root + blocks 1-2 (activation working set vs. L2)
     late_chunk: int = 640         # frames per pass of ResNet blocks 3-4 (small maps: batch wide to fill 148 SMs)
     extra: dict = field(default_factory=dict)
