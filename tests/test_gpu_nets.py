@@ -266,7 +266,10 @@ def test_tester_surface_and_sliding_window(weights, smpl_model):
     tester = Tester(cfg)
     N = 19                                        # -> count = ceil(19 / (8*2)) = 2 passes, ragged tail
     frames = synthetic.make_images(N, seed=9, size=S)
-    res = tester.predict_all_images(frames)
+    res = tester.predict_all_images(frames)                         # cached per-frame features (default)
+    res_literal = tester.predict_all_images(frames, cache_features=False)   # the reference's literal image windows
+    for k in res:
+        assert np.array_equal(res[k], res_literal[k]), 'feature cache changed ' + k
     margin, g = 6, 8
     count = int(np.ceil(N / (g * B)))
     padded = np.concatenate([np.zeros((margin, S, S, 3), np.float32), frames,
