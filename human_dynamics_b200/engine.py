@@ -11,9 +11,9 @@ import torch
 
 from . import _lib
 from .config import HMMRConfig
-from .nets import (FMoviePlan, IEFPlan, PackedConv, PackedFMovie, PackedIEF, PackedResNet, ResNetPlan, _dev)
+from .nets import FMoviePlan, IEFPlan, PackedConv, PackedFMovie, PackedIEF, PackedResNet, ResNetPlan
 from .smpl import SMPLConstants
-from ._lib import lib, current_stream
+from ._lib import current_stream
 
 
 def load_weights(path_or_dict):

@@ -7,7 +7,6 @@ Weights come in as a dict of numpy arrays keyed by TF variable names (SURVEY.md 
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 import torch

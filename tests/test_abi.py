@@ -84,3 +84,32 @@ def test_conv_desc_matches_compiled_struct():
     assert out[0] == ctypes.sizeof(_lib.ConvDesc) and out[1] == ctypes.sizeof(_lib.SmplConsts)
     for f, off in zip(fields, out[2:]):
         assert getattr(_lib.ConvDesc, f).offset == off, f
+
+
+def test_host_logic_without_gpu():
+    """Pure host logic of the plan / driver layer (no device needed)."""
+    import types
+    import pytest
+    from human_dynamics_b200.engine import HMMREngine
+    from human_dynamics_b200 import HMMRConfig
+    fake = types.SimpleNamespace(config=HMMRConfig(frame_chunk=160), H2D_PIECE=HMMREngine.H2D_PIECE)
+    sched = HMMREngine.stage_a_schedule(fake, 640, True)            # streaming from the host: small first pass
+    assert sched[0] == (0, 32) and sum(n for _, n in sched) == 640 and all(n <= 160 for _, n in sched)
+    assert [s for s, _ in sched] == [0] + [32 + 160 * i for i in range(4)]
+    assert HMMREngine.stage_a_schedule(fake, 640, False) == [(0, 160), (160, 160), (320, 160), (480, 160)]
+    assert HMMREngine.stage_a_schedule(fake, 20, True) == [(0, 20)]
+    # Tester refuses to start without weights, like the reference (tester.py:31-38), but without ipdb
+    from src.evaluation.tester import Tester
+    with pytest.raises(Exception):
+        Tester(HMMRConfig(load_path=''))
+    with pytest.raises(Exception):
+        Tester(HMMRConfig(load_path='/nonexistent/model.npz'))
+    # TF-style SAME / conv2d_same output sizes used by the plans
+    from human_dynamics_b200.nets import f16_split, tf32_split
+    import numpy as np
+    w = np.random.RandomState(0).normal(0, 0.05, size=(7, 5)).astype(np.float32)
+    hi, lo = f16_split(w)
+    assert np.abs(hi.astype(np.float64) + lo.astype(np.float64) / 2048.0 - w).max() < 2.0 ** -22 * np.abs(w).max() * 2
+    th, tl = tf32_split(w)
+    assert np.all((th.view(np.uint32) & 0x1FFF) == 0) and np.all((tl.view(np.uint32) & 0x1FFF) == 0)
+    assert np.abs(th.astype(np.float64) + tl.astype(np.float64) - w).max() < 2.0 ** -21 * np.abs(w).max()
