@@ -16,15 +16,39 @@ from ._lib import lib, check, fptr, dptr, current_stream
 
 
 def _dense(m):
-    m = m.r if hasattr(m, 'r') and not isinstance(m, np.ndarray) else m      # undo_chumpy, batch_smpl.py:22-23
+    m = m.r if (hasattr(m, 'r') and not isinstance(m, np.ndarray) and not hasattr(m, 'todense')) else m   # undo_chumpy, batch_smpl.py:22-23
     return np.asarray(m.todense()) if hasattr(m, 'todense') else np.asarray(m)
 
 
+class _ChStub(object):
+    """Stand-in for chumpy objects inside the official SMPL pickles (chumpy is not a dependency here).
+
+    chumpy.Ch pickles as (class, state-dict) with the wrapped ndarray under 'x'; the reference reads it through `.r`
+    (`undo_chumpy`, batch_smpl.py:22-23).  Any other attribute of the state is kept but unused."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {'x': state})
+
+    @property
+    def r(self):
+        return np.asarray(self.__dict__['x'])
+
+
+class _SMPLUnpickler(pickle.Unpickler):
+    """pickle.Unpickler that maps every class from the `chumpy` package to `_ChStub` (scipy.sparse / numpy load normally)."""
+
+    def find_class(self, module, name):
+        if module == 'chumpy' or module.startswith('chumpy.'):
+            return _ChStub
+        return super().find_class(module, name)
+
+
 def load_smpl_model(pkl_path_or_dict):
+    """The un-pickled SMPL model dict (batch_smpl.py:31-32: `pickle.load(f, encoding='latin1')`), without needing chumpy."""
     if isinstance(pkl_path_or_dict, dict):
         return pkl_path_or_dict
     with open(pkl_path_or_dict, 'rb') as f:
-        return pickle.load(f, encoding='latin1')                              # batch_smpl.py:31-32
+        return _SMPLUnpickler(f, encoding='latin1').load()
 
 
 class SMPLConstants(object):
