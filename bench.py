@@ -96,7 +96,14 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference path on the host cores
 # --------------------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, clips_per_step=1, T=20):
+PARITY_KEYS = ('omegas', 'verts', 'kps', 'joints', 'poses', 'omegas_delta', 'verts_delta', 'kps_delta')
+PARITY_TOL = 1e-4          # BASELINE.json north_star: outputs within 1e-4 rel FP32 of the reference graph
+
+
+def cpu_reference_run(workload, steps, warmup, clips_per_step=1, T=20, images=None, keep=None):
+    """Times the oracle port on the host cores.  `images` (optional, hmmr / single_frame): run on exactly these frames
+    instead of a fresh synthetic sample; `keep` (a dict) then receives the oracle's outputs of the last step, which is how
+    bench.py parity-checks the run it has just timed (the checker, never the thing measured as ours)."""
     import torch
     from human_dynamics_b200 import synthetic
     from oracle import nets_ref
@@ -121,21 +128,26 @@ def cpu_reference_run(workload, steps, warmup, clips_per_step=1, T=20):
                 times.append(time.perf_counter() - t0)
         units, sample = n, '%d poses per step (numpy float32 port of batch_smpl.py)' % n
     elif workload == 'single_frame':
-        n = 8
-        img = synthetic.make_images(n, seed=0)
+        img = synthetic.make_images(8, seed=0) if images is None else images
+        n = img.shape[0]
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            nets_ref.single_frame_predict(img, w, smpl)
+            r = nets_ref.single_frame_predict(img, w, smpl)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+        if keep is not None:
+            keep.update(r)
         units, sample = n, '%d frames per step (torch-CPU float32 port, reference op order)' % n
     else:
-        img = synthetic.make_images(clips_per_step * T, seed=0).reshape(clips_per_step, T, 224, 224, 3)
+        img = synthetic.make_images(clips_per_step * T, seed=0).reshape(clips_per_step, T, 224, 224, 3) if images is None else images
+        clips_per_step = img.shape[0]
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            nets_ref.hmmr_predict(img, w, smpl)
+            r = nets_ref.hmmr_predict(img, w, smpl)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+        if keep is not None:
+            keep.update(r)
         units = clips_per_step * T
         sample = '%d clip(s) x T=%d frames per step (torch-CPU float32 port of the TF1 graph, reference op order)' % (clips_per_step, T)
     sec = float(np.mean(times))
@@ -228,6 +240,7 @@ def main():
 
         def step():
             out = eng.predict(img_dev, single_frame=single)
+            last['out'] = out
             if world > 1:
                 last['g'] = gather_outputs({k: out[k] for k in gather_keys}, B * world, dst=0)
 
@@ -285,10 +298,35 @@ def main():
     if rank == 0:
         roofline = measure_roofline(args, peaks, locals())
 
-    cpu_baseline = None
+    # ------------------------------------------------------------------ cpu_baseline + parity of the run just timed
+    # The oracle port runs on the FIRST and LAST clip (frame) of this very benchmark input; its outputs double as the
+    # checker of the last timed step's results (clips / frames are independent, so a 2-clip oracle run checks them exactly).
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, sample = cpu_reference_run(args.workload, 2, 1)
+        if args.workload == 'smpl':
+            v, sec, cores, sample = cpu_reference_run(args.workload, 2, 1)
+        else:
+            sel = [0, B - 1]
+            sub = img_host[sel].numpy() if not single else img_host[sel].numpy().reshape(2, 224, 224, 3)
+            ref = {}
+            v, sec, cores, sample = cpu_reference_run(args.workload, 2, 1, images=sub, keep=ref)
+            torch.cuda.synchronize()
+            worst, per = 0.0, {}
+            for k in PARITY_KEYS:
+                if k not in ref or k not in last['out']:
+                    continue
+                g = last['out'][k][sel].float().cpu().numpy().reshape(ref[k].shape).astype(np.float64)
+                e = float(np.abs(g - ref[k]).max() / max(float(np.abs(ref[k]).max()), 1e-12))
+                per[k] = e
+                worst = max(worst, e)
+            parity = {'parity_max_rel': worst, 'tolerance': PARITY_TOL, 'per_key': per,
+                      'checked': 'last timed step, %s {0, %d} of %d vs the float32 oracle port' % ('frames' if single else 'clips', B - 1, B)}
+            sample += ' = %s {0, %d} of the timed input' % ('frames' if single else 'clips', B - 1)
         cpu_baseline = {'value': v, 'unit': unit_name, 'cores': cores, 'kind': 'port', 'sample': sample}
+    if rank == 0 and world > 1 and last.get('g') is not None:
+        # gathered tensors must contain rank 0's own clips bit for bit (the N-GPU == 1-GPU identity is tests/test_multi_gpu.py)
+        ok = all(torch.equal(last['g'][k][:B], last['out'][k]) for k in gather_keys)
+        parity = {'gather_own_shard_bit_identical': bool(ok)}
 
     if rank == 0:
         line = {'metric': metric, 'value': value, 'unit': unit_name, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -309,7 +347,17 @@ def main():
             line['roofline'] = roofline
         if cpu_baseline:
             line['cpu_baseline'] = cpu_baseline
+        if parity:
+            line['parity'] = parity
+            if 'parity_max_rel' in parity:
+                line['parity_max_rel'] = parity['parity_max_rel']
         print(json.dumps(line))
+        if parity and parity.get('parity_max_rel', 0.0) > PARITY_TOL:
+            sys.stderr.write('bench.py: PARITY FAILURE %r\n' % (parity,))
+            return 3
+        if parity and parity.get('gather_own_shard_bit_identical') is False:
+            sys.stderr.write('bench.py: gathered outputs differ from the local shard\n')
+            return 3
     if world > 1:
         dist.destroy_process_group()
     return 0

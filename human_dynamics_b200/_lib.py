@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhd_b200.so')
 
 HD_IMPL_SIMT, HD_IMPL_TC_3XTF32, HD_IMPL_TC_1XTF32, HD_IMPL_TC_3XF16 = 0, 1, 2, 3
+HD_CONV_NO_TMA_EPILOGUE = 1
 IMPL_BY_NAME = {'simt': HD_IMPL_SIMT, 'tc3': HD_IMPL_TC_3XTF32, 'tc1': HD_IMPL_TC_1XTF32, 'tc3h': HD_IMPL_TC_3XF16}
 
 
@@ -33,6 +34,8 @@ class ConvDesc(C.Structure):
         ('in_hi', C.c_void_p), ('in_lo', C.c_void_p),
         ('out_hi', C.c_void_p), ('out_lo', C.c_void_p), ('out2_ld', C.c_longlong),
         ('post2_scale', C.c_void_p), ('post2_shift', C.c_void_p), ('post2_relu', C.c_int),
+        ('tmap_res', C.c_void_p), ('tmap_out', C.c_void_p), ('tmap_out_hi', C.c_void_p), ('tmap_out_lo', C.c_void_p),
+        ('flags', C.c_int),
     ]
 
 
@@ -58,6 +61,7 @@ SIGNATURES = {
     'hd_conv_gemm': (_i, [C.POINTER(ConvDesc), _vp]),
     'hd_conv_gemm_profile': (_i, [C.POINTER(ConvDesc), _vp, _vp]),
     'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _i, _vp]),
+    'hd_make_act_tmap': (_i, [_vp, _ll, _i, _ll, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -1,5 +1,6 @@
 // Device-side parameter block shared by the SIMT and tcgen05 implicit-GEMM kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace hd {
@@ -19,6 +20,21 @@ struct ConvParams {
   const float *post2_scale, *post2_shift; int post2_relu;
   long long *dbg;  // optional: per-role cycle counters of CTA (0,0) (hd_conv_gemm_profile), else nullptr
 };
+
+#ifdef __CUDACC__
+// (a0, a1) -> packed fp16 heads hi = RN_f16(a) and 2^11-scaled remainders lo = RN_f16((a - hi) * 2^11): the operand format of
+// the fp16-split tensor-core path.  The value is first clamped to the finite fp16 range: an activation beyond +-65504 then
+// saturates (hi = +-65504, lo = 0) instead of turning into inf / NaN that would spread through the trunk.
+__device__ __forceinline__ void split_f16x2(float a0, float a1, uint32_t &hi, uint32_t &lo) {
+  a0 = fminf(fmaxf(a0, -65504.f), 65504.f);
+  a1 = fminf(fmaxf(a1, -65504.f), 65504.f);
+  const __half2 h2 = __floats2half2_rn(a0, a1);
+  const float2 f2 = __half22float2(h2);
+  const __half2 l2 = __floats2half2_rn((a0 - f2.x) * 2048.0f, (a1 - f2.y) * 2048.0f);
+  hi = *reinterpret_cast<const uint32_t *>(&h2);
+  lo = *reinterpret_cast<const uint32_t *>(&l2);
+}
+#endif
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -62,6 +62,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
@@ -121,11 +134,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-template <int BN, bool HALF, bool DUAL = false>
+// TEPI (TMA epilogue; K <= 256, i.e. the HBM-shaped 1x1 layers): one drain group whose threads own accumulator rows and
+// only ever touch shared memory; the residual arrives and fp32 / fp16-pair outputs leave as 128-row x 32-column slabs
+// moved by TMA (cp.async.bulk.tensor load / store) through a ring of three swizzled staging buffers.
+template <int BN, bool HALF, bool DUAL = false, bool TEPI = false>
 struct Cfg {
   // DUAL (epilogue-bound layers, K <= 256, one drain group per tile): two drain/epilogue warp groups take alternate tiles;
   // the main loop is short there, so 2 operand stages suffice and pay for the second set of staging tiles.
-  static constexpr int STAGES = DUAL ? 2 : 3;
+  static constexpr int STAGES = (DUAL || TEPI) ? 2 : 3;
   static constexpr int DW = DUAL ? 8 : 4;                       // drain + epilogue warps
   static constexpr int NUM_THREADS = (DW + 8 + 4) * 32;         // + 8 producer warps + {TMA, MMA, 2 idle}
   static constexpr int BKE = HALF ? 64 : 32;                    // K elements per chunk (one 128-byte row)
@@ -138,7 +154,13 @@ struct Cfg {
   static constexpr int NSTG = DUAL ? 2 : 1;                     // DUAL has the smem for double-buffered residual slabs
   static constexpr int STG_BYTES = DW * NSTG * 32 * STG_LD * 4; // 32 x 32 tile(s) per drain warp
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
-  static constexpr int SMEM_BYTES = LUT_OFFSET + 1024 + 1024;   // + alignment slack
+  // TEPI staging ring: per buffer one fp32 slab [128][32] (128-byte rows, SWIZZLE_128B) + two fp16 slabs [128][32]
+  // (64-byte rows, SWIZZLE_64B); 1024-byte aligned
+  static constexpr int EPI_NB = 3;
+  static constexpr int EPI_F32_BYTES = 128 * 128, EPI_H_BYTES = 128 * 64;
+  static constexpr int EPI_BUF_BYTES = EPI_F32_BYTES + 2 * EPI_H_BYTES;
+  static constexpr int EPI_OFFSET = (BAR_OFFSET + 128 + 1023) / 1024 * 1024;
+  static constexpr int SMEM_BYTES = TEPI ? EPI_OFFSET + EPI_NB * EPI_BUF_BYTES + 1024 : LUT_OFFSET + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
   // D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10), b_format[10,13) (2 = TF32, 0 = F16), N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t FMT = HALF ? 0u : 2u;
@@ -151,10 +173,15 @@ struct RowState {       // 4 output rows of one producer thread: image index and
   int n[4], iy[4], ix[4];
 };
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT, bool DUAL>
-__global__ void __launch_bounds__((Cfg<BN, HALF, DUAL>::NUM_THREADS), 1)
-conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo) {
-  using C = Cfg<BN, HALF, DUAL>;
+struct EpiMaps {      // TEPI only: activation tensor maps (fp32 residual / output, fp16 head / remainder outputs)
+  CUtensorMap res, out, ohi, olo;
+};
+
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT, bool DUAL, bool TEPI>
+__global__ void __launch_bounds__((Cfg<BN, HALF, DUAL, TEPI>::NUM_THREADS), 1)
+conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+                    const __grid_constant__ EpiMaps em) {
+  using C = Cfg<BN, HALF, DUAL, TEPI>;
   constexpr int BKE = C::BKE, PF = C::PF, V = C::V, STAGES = C::STAGES, DW = C::DW, NUM_THREADS = C::NUM_THREADS;
   constexpr int W_TMA = DW + 8, W_MMA = DW + 9;
   extern __shared__ uint8_t smem_raw[];
@@ -167,6 +194,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };    // accumulator b drained
   auto smallf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };  // cross-term accumulator b drained
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };     // TEPI: residual slab landed in ring buffer b
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (GATHER ? p.K_pad : p.K) / BKE;   // GATHER: ragged Cin (conv1: K=147 zero-padded to 192)
@@ -186,6 +214,8 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       mbar_init(acce_bar(b), 4);     // one lane per drain warp
       mbar_init(smallf_bar(b), 4);
     }
+    if (TEPI)
+      for (int b = 0; b < C::EPI_NB; ++b) mbar_init(res_bar(b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_TMA) {
@@ -202,6 +232,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   if (warp >= DW && warp < DW + 8) {
     // =============================== A producers (256 threads) ===============================
     if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    else if (TEPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int t = threadIdx.x - DW * 32;  // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
@@ -365,13 +396,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __half2 hh = __floats2half2_rn(xs[2 * e], xs[2 * e + 1]);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn((xs[2 * e] - hf.x) * 2048.0f, (xs[2 * e + 1] - hf.y) * 2048.0f);
-            h[e] = *reinterpret_cast<const uint32_t *>(&hh);
-            l[e] = *reinterpret_cast<const uint32_t *>(&ll);
-          }
+          for (int e = 0; e < 4; ++e) split_f16x2(xs[2 * e], xs[2 * e + 1], h[e], l[e]);
         }
         const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
         if (xmode & 1) continue;
@@ -403,19 +428,38 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     // =============================== drain + epilogue ===============================
     const int dgroup = warp >> 2, quarter = warp & 3;     // DUAL: group 0 takes even tiles, group 1 odd tiles
     if (DUAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    else if (TEPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
     float *stg0 = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::NSTG * 32 * C::STG_LD);
     const int hw = p.Ho * p.Wo;
+    // ---- TEPI: residual slab loads run one slab ahead of the math, issued by the group leader (thread 0) ----
+    const bool epi_leader = threadIdx.x == 0;
+    auto epi_issue_res = [&](int j) {          // residual of global slab j (tile j / NSL of this CTA, slab j % NSL) -> ring buffer j % NB
+      constexpr int NSLq = BN / 32;
+      const int tj = j / NSLq;
+      if (tj >= my_tiles) return;
+      const int tile = (int)blockIdx.x + tj * (int)gridDim.x;
+      const int b = j % C::EPI_NB;
+      mbar_arrive_expect_tx(res_bar(b), C::EPI_F32_BYTES);
+      tma_load_2d(smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES, &em.res, res_bar(b), (tile % tiles_n) * BN + (j % NSLq) * 32,
+                  (tile / tiles_n) * BM);
+    };
+    if (TEPI && epi_leader && p.res) epi_issue_res(0);
     for (int ti = dgroup; ti < my_tiles; ti += (DUAL ? 2 : 1)) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       float sums[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) sums[i] = 0.f;
-      if (p.res && p.vec_out) {       // pull the residual rows of this group's NEXT tile towards L2 (a whole tile period of lead
+      if (TEPI) {
+        if (epi_leader && p.res && ti + 1 < my_tiles) {      // next tile's residual slabs -> L2, a whole tile period ahead
+          const int tilen = (int)blockIdx.x + (ti + 1) * (int)gridDim.x;
+          for (int sl = 0; sl < BN / 32; ++sl) tma_prefetch_2d(&em.res, (tilen % tiles_n) * BN + sl * 32, (tilen / tiles_n) * BM);
+        }
+      } else if (p.res && p.vec_out) {       // pull the residual rows of this group's NEXT tile towards L2 (a whole tile period of lead
                                       // time; the very first tile is prefetched on entry), so the epilogue's cp.asyncs hit L2
         const int tstep = DUAL ? 2 : 1;
         const int tin = (ti == dgroup) ? ti : ti + tstep;                 // first iteration: this tile
@@ -467,6 +511,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         if (lane == 0) mbar_arrive(smallf_bar(sb));
       }
       long long te0 = prof ? clock64() : 0;
+      if constexpr (!TEPI) {
       // Epilogue (overlaps the next tile's main loop).  Each lane owns one accumulator ROW (TMEM lane) but global memory
       // wants a warp to touch contiguous columns of a row.  Per 32-column slab: the residual slab is fetched by cp.async
       // straight into the warp's padded 32 x 32 smem tile (no registers), every lane adds its 32 accumulator values into its
@@ -572,14 +617,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             if (st16) {          // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
               float y0 = x0 * qsc.x + qsh.x, y1 = x1 * qsc.y + qsh.y, y2 = x2 * qsc.z + qsh.z, y3 = x3 * qsc.w + qsh.w;
               if (p.post2_relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
-              const __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-              const __half2 l0 = __floats2half2_rn((y0 - f0.x) * 2048.0f, (y1 - f0.y) * 2048.0f);
-              const __half2 l1 = __floats2half2_rn((y2 - f1.x) * 2048.0f, (y3 - f1.y) * 2048.0f);
-              *reinterpret_cast<uint2 *>(ohp + i * hstep) =
-                  make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-              *reinterpret_cast<uint2 *>(olp + i * hstep) =
-                  make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+              uint32_t h0, h1, l0, l1;
+              split_f16x2(y0, y1, h0, l0);
+              split_f16x2(y2, y3, h1, l1);
+              *reinterpret_cast<uint2 *>(ohp + i * hstep) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(olp + i * hstep) = make_uint2(l0, l1);
             }
           } else {             // ragged / unaligned outputs (IEF 85- and 72-wide heads): element-wise
             const float av[4] = {a.x, a.y, a.z, a.w};
@@ -600,6 +642,91 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
               if (p.post_relu) y = fmaxf(y, 0.f);
               p.out[(size_t)m * p.out_ld + co + e] = y;
             }
+          }
+        }
+      }
+      } else {
+        // ---- TMA epilogue: thread = accumulator row (TMEM lane); per 32-column slab: wait for the residual slab (TMA load,
+        // issued one slab ahead), v = acc*scale + shift (+ residual) (ReLU) in place in the swizzled staging buffer, the next
+        // layer's pre-activated fp16 head/remainder beside it, then one thread hands the three slabs to TMA stores. ----
+        constexpr int NSL = BN / 32, NB = C::EPI_NB;
+        const int row = quarter * 32 + lane;
+        const uint32_t sw128 = (uint32_t)(row & 7), sw64 = (uint32_t)((row >> 1) & 3);
+        const bool has_res = p.res != nullptr, has_o32 = p.out != nullptr, has_o16 = p.out_hi != nullptr;
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          const int gi = ti * NSL + sl;                 // running slab index of this CTA
+          const int b = gi % NB;
+          uint8_t *buf = smem + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
+          if (epi_leader) {
+            bulk_wait_read<NB - 2>();                   // the stores of slab gi-2 have read their buffer = buffer (gi+1) % NB
+            if (has_res) epi_issue_res(gi + 1);
+          }
+          if (has_res) mbar_wait(res_bar(b), (uint32_t)(gi / NB) & 1u);
+          uint8_t *frow = buf + row * 128;
+          uint8_t *hrow = buf + C::EPI_F32_BYTES + row * 64;
+          uint8_t *lrow = hrow + C::EPI_H_BYTES;
+          const int cb = n0 + sl * 32;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {                 // 8 columns: two fp32 chunks, one fp16 chunk
+            float y[8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = 2 * h + q;
+              float4 v = make_float4(sums[sl * 32 + 4 * c], sums[sl * 32 + 4 * c + 1], sums[sl * 32 + 4 * c + 2], sums[sl * 32 + 4 * c + 3]);
+              if (p.post_scale) {
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(p.post_scale + cb + 4 * c));
+                v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+              }
+              if (p.post_shift) {
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(p.post_shift + cb + 4 * c));
+                v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+              }
+              float4 *sp = reinterpret_cast<float4 *>(frow + (((uint32_t)c ^ sw128) << 4));
+              if (has_res) {
+                const float4 r = *sp;
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+              }
+              if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (has_o32) *sp = v;
+              y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+            }
+            if (has_o16) {       // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
+              if (p.post2_scale) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const float4 s = __ldg(reinterpret_cast<const float4 *>(p.post2_scale + cb + 8 * h + 4 * q));
+                  y[4 * q] *= s.x; y[4 * q + 1] *= s.y; y[4 * q + 2] *= s.z; y[4 * q + 3] *= s.w;
+                }
+              }
+              if (p.post2_shift) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const float4 s = __ldg(reinterpret_cast<const float4 *>(p.post2_shift + cb + 8 * h + 4 * q));
+                  y[4 * q] += s.x; y[4 * q + 1] += s.y; y[4 * q + 2] += s.z; y[4 * q + 3] += s.w;
+                }
+              }
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = y[2 * e], a1 = y[2 * e + 1];
+                if (p.post2_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                split_f16x2(a0, a1, hh[e], ll[e]);
+              }
+              *reinterpret_cast<uint4 *>(hrow + (((uint32_t)h ^ sw64) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4 *>(lrow + (((uint32_t)h ^ sw64) << 4)) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the TMA store
+          named_bar_sync(1, 128);
+          if (epi_leader) {
+            const uint32_t sb = smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
+            if (has_o32) tma_store_2d(&em.out, sb, cb, m0);
+            if (has_o16) {
+              tma_store_2d(&em.ohi, sb + C::EPI_F32_BYTES, cb, m0);
+              tma_store_2d(&em.olo, sb + C::EPI_F32_BYTES + C::EPI_H_BYTES, cb, m0);
+            }
+            bulk_commit();
           }
         }
       }
@@ -691,6 +818,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     }
   }
+  if (TEPI && threadIdx.x == 0) bulk_wait_read<0>();     // the last TMA stores have read their staging buffers
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == W_TMA) {
@@ -717,28 +845,42 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false, bool DUAL = false>
+constexpr int kMaxDevices = 64;
+
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false, bool DUAL = false, bool TEPI = false>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
-  using C = Cfg<BN, HALF, DUAL>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  using C = Cfg<BN, HALF, DUAL, TEPI>;
+  // function attributes and the SM count are per device: a process may drive several GPUs through this library
+  static bool configured[kMaxDevices] = {};
+  static int num_sms[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) { set_last_error_text("conv_gemm_tc: device ordinal out of range"); return HD_ERR_UNSUPPORTED; }
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL, TEPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("conv_gemm_tc attr", e); return HD_ERR_CUDA; }
-    configured = true;
+    cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms[dev] <= 0) num_sms[dev] = 148;
+    configured[dev] = true;
   }
   alignas(64) CUtensorMap thi, tlo;
   memcpy(&thi, d->tmap_hi, sizeof(CUtensorMap));
   memcpy(&tlo, d->tmap_lo ? d->tmap_lo : d->tmap_hi, sizeof(CUtensorMap));
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
+  alignas(64) EpiMaps em;
+  if (TEPI) {      // absent maps are never dereferenced by the kernel (guarded by the same null tests on p.res / p.out / p.out_hi)
+    const void *any = d->tmap_out ? d->tmap_out : d->tmap_out_hi;
+    memcpy(&em.res, d->tmap_res ? d->tmap_res : any, sizeof(CUtensorMap));
+    memcpy(&em.out, d->tmap_out ? d->tmap_out : any, sizeof(CUtensorMap));
+    memcpy(&em.ohi, d->tmap_out_hi ? d->tmap_out_hi : any, sizeof(CUtensorMap));
+    memcpy(&em.olo, d->tmap_out_lo ? d->tmap_out_lo : any, sizeof(CUtensorMap));
+  } else {
+    memcpy(&em.res, &thi, sizeof(CUtensorMap)); memcpy(&em.out, &thi, sizeof(CUtensorMap));
+    memcpy(&em.ohi, &thi, sizeof(CUtensorMap)); memcpy(&em.olo, &thi, sizeof(CUtensorMap));
   }
   const int num_tiles = ceil_div(p.M, BM) * ceil_div(p.Cout, BN);
-  dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);     // persistent: one CTA per SM walks the tile list
-  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL><<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo);
+  dim3 grid(num_tiles < num_sms[dev] ? num_tiles : num_sms[dev]);     // persistent: one CTA per SM walks the tile list
+  conv_gemm_tc_kernel<BN, SPLIT, PCH, HALF, GATHER, ASPLIT, DUAL, TEPI><<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(p, thi, tlo, em);
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -760,8 +902,15 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       set_last_error_text("hd_conv_gemm(tc split-A): needs Cin % 64 == 0, in_ld % 8 == 0, aligned in_hi/in_lo, no prologue");
       return HD_ERR_INVALID;
     }
-    if (p.K <= 256)      // epilogue-bound layers: one drain group per tile (<= 16 MMAs per accumulator), two drain/epilogue warp groups
+    if (p.K <= 256) {    // HBM-shaped layers: one drain group per tile (<= 16 MMAs per accumulator)
+      const bool res_plain = !p.res || (p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo);
+      const bool maps = (!p.res || d->tmap_res) && (!p.out || d->tmap_out) && (!p.out_hi || (d->tmap_out_hi && d->tmap_out_lo));
+      if (maps && res_plain && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE))     // TMA epilogue
+        return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, false, true>(p, d, st)
+                            : launch_tc<128, true, 4, true, false, true, false, true>(p, d, st);
+      // strided-subsample residuals / no tensor maps: two drain/epilogue warp groups with per-thread global accesses
       return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);
+    }
     return p.Cout <= 64 ? launch_tc<64, true, 2, true, false, true>(p, d, st) : launch_tc<128, true, 2, true, false, true>(p, d, st);
   }
   if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded
@@ -807,6 +956,32 @@ extern "C" int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int bo
   if (r != CUDA_SUCCESS) {
     char msg[96];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    hd::set_last_error_text(msg);
+    return HD_ERR_CUDA;
+  }
+  memcpy(tmap_out, &tm, sizeof(tm));
+  return HD_OK;
+}
+
+// Row-major activation matrix [rows, cols] (leading dimension ld_elems; fp32 or fp16) -> CUtensorMap with a {32 columns x 128 rows}
+// box: the slab the TMA epilogue loads (residual) / stores (outputs).  fp32 slabs use the 128-byte swizzle, fp16 slabs the 64-byte one.
+extern "C" int hd_make_act_tmap(const void *base, long long rows, int cols, long long ld_elems, int elem_bytes, void *tmap_out) {
+  HD_REQUIRE(base && tmap_out && rows > 0 && cols > 0 && ld_elems >= cols && (elem_bytes == 4 || elem_bytes == 2) && hd::aligned16(base) &&
+                 (ld_elems * elem_bytes) % 16 == 0,
+             "hd_make_act_tmap: bad arguments (16-byte aligned base and row pitch required)");
+  hd::EncodeTiledFn fn = hd::get_encode_fn();
+  if (!fn) { hd::set_last_error_text("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return HD_ERR_UNSUPPORTED; }
+  alignas(64) CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {32u, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(&tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (activation) failed with CUresult %d", (int)r);
     hd::set_last_error_text(msg);
     return HD_ERR_CUDA;
   }

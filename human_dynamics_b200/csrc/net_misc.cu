@@ -36,13 +36,7 @@ __global__ void maxpool3x3s2_kernel(const float4 *__restrict__ in, float4 *__res
                         fmaxf(m.w * sc.w + sh.w, 0.f)};
     uint32_t hp[2], lp[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const __half2 hh = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
-      const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn((y[2 * e] - hf.x) * 2048.0f, (y[2 * e + 1] - hf.y) * 2048.0f);
-      hp[e] = *reinterpret_cast<const uint32_t *>(&hh);
-      lp[e] = *reinterpret_cast<const uint32_t *>(&ll);
-    }
+    for (int e = 0; e < 2; ++e) hd::split_f16x2(y[2 * e], y[2 * e + 1], hp[e], lp[e]);
     out_hi[i] = make_uint2(hp[0], hp[1]);
     out_lo[i] = make_uint2(lp[0], lp[1]);
   }

@@ -7,6 +7,7 @@ Weights come in as a dict of numpy arrays keyed by TF variable names (SURVEY.md 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -172,15 +173,55 @@ class PackedConv(object):
             d.tmap_lo = C.cast(self.tmap_lo, C.c_void_p)
         else:
             d.impl = _lib.HD_IMPL_SIMT
-        return ConvOp(d, (self, inp, out, pre, res, inp_split, out_split, post2), (Ho, Wo))
+        op = ConvOp(d, (self, inp, out, pre, res, inp_split, out_split, post2), (Ho, Wo))
+        if not TMA_EPILOGUE:
+            d.flags |= _lib.HD_CONV_NO_TMA_EPILOGUE
+        op.encode_act_maps()
+        return op
+
+
+TMA_EPILOGUE = os.environ.get('HD_TMA_EPILOGUE', '1') != '0'     # A/B switch for the K <= 256 layers (results identical)
 
 
 class ConvOp(object):
-    __slots__ = ('d', 'keep', 'out_hw', 'ref')
+    __slots__ = ('d', 'keep', 'out_hw', 'ref', 'dyn', 'maps')
 
     def __init__(self, d, keep, out_hw):
         self.d, self.keep, self.out_hw = d, keep, out_hw
         self.ref = C.byref(d)
+        self.dyn = {}           # descriptor field -> tensor it currently points at (rebinding overwrites, never appends)
+        self.maps = None
+
+    def encode_act_maps(self):
+        """(Re-)encode the activation tensor maps of the TMA epilogue for the pointers currently in the descriptor.
+        Only layers the kernel can run that way get maps (conv_tc.cu launch_conv_tc): fp16-split input, K <= 256,
+        Cout % 32 == 0, residual row == output row; everything else keeps the per-thread epilogue."""
+        d = self.d
+        K = d.KH * d.KW * d.Cin
+        ok = (d.impl == _lib.HD_IMPL_TC_3XF16 and d.in_hi and K <= 256 and d.Cout % 32 == 0 and
+              (not d.res or (d.res_stride == 1 and d.res_H == d.Ho and d.res_W == d.Wo)))
+        for f in ('tmap_res', 'tmap_out', 'tmap_out_hi', 'tmap_out_lo'):
+            setattr(d, f, None)
+        if not ok:
+            return
+        M = d.n_img * d.Ho * d.Wo
+        if self.maps is None:
+            self.maps = {f: (C.c_ubyte * 128)() for f in ('res', 'out', 'out_hi', 'out_lo')}
+        for f, ptr, ld, eb in (('res', d.res, d.res_ld, 4), ('out', d.out, d.out_ld, 4), ('out_hi', d.out_hi, d.out2_ld, 2),
+                               ('out_lo', d.out_lo, d.out2_ld, 2)):
+            if not ptr:
+                continue
+            if ptr % 16 or (ld * eb) % 16:
+                for g in ('tmap_res', 'tmap_out', 'tmap_out_hi', 'tmap_out_lo'):
+                    setattr(d, g, None)
+                return
+            check(lib.hd_make_act_tmap(C.c_void_p(ptr), M, d.Cout, ld, eb, C.cast(self.maps[f], C.c_void_p)), 'hd_make_act_tmap')
+            setattr(d, 'tmap_' + f, C.cast(self.maps[f], C.c_void_p))
+
+    def rebind(self, field, tensor):
+        """Point one descriptor field at another tensor (stage input / output of a cached plan)."""
+        setattr(self.d, field, tensor.data_ptr())
+        self.dyn[field] = tensor
 
     def run(self, stream):
         rc = lib.hd_conv_gemm(self.ref, stream)
@@ -351,18 +392,19 @@ class ResNetPlan(object):
             src = srcs[which]
             if src is None:
                 raise _lib.HDError('stage input %s missing' % field)
-            setattr(op.d, field, src.data_ptr())
-            op.keep = op.keep + (src,)
+            op.rebind(field, src)
+        for op in {id(o): o for o, _, _ in self.in_refs}.values():
+            op.encode_act_maps()
 
     def set_output(self, t, t_split=None):
         """Let the last unit write its output feature map [n, out_hw, out_hw, out_depth] straight into `t` (and, in split
         mode, the next stage's pre-activated pair into `t_split`)."""
         op = self.ops[-1]
-        op.d.out = t.data_ptr()
-        op.keep = op.keep + (t,)
+        op.rebind('out', t)
         if t_split is not None:
-            op.d.out_hi, op.d.out_lo = t_split[0].data_ptr(), t_split[1].data_ptr()
-            op.keep = op.keep + tuple(t_split)
+            op.rebind('out_hi', t_split[0])
+            op.rebind('out_lo', t_split[1])
+        op.encode_act_maps()
         self.final = t
 
     def run(self, images, out, stream=None):

@@ -79,7 +79,15 @@ typedef struct {
   const void *in_hi, *in_lo;
   void *out_hi, *out_lo;  long long out2_ld;
   const float *post2_scale, *post2_shift;  int post2_relu;
+  /* TMA epilogue (impl 3, pre-split input, K <= 256, Cout % 32 == 0, residual row == output row): HOST pointers to 128-byte
+   * CUtensorMap blobs from hd_make_act_tmap over `res`, `out`, `out_hi`, `out_lo` (each required iff that pointer is set).
+   * When given, the residual is loaded and all outputs are stored as 128-row x 32-column slabs by TMA; otherwise (or with
+   * HD_CONV_NO_TMA_EPILOGUE in `flags`) the epilogue uses per-thread global accesses.  Results are identical. */
+  const void *tmap_res, *tmap_out, *tmap_out_hi, *tmap_out_lo;
+  int flags;
 } hd_conv_desc;
+
+enum { HD_CONV_NO_TMA_EPILOGUE = 1 };
 
 int hd_conv_gemm(const hd_conv_desc *d, void *stream);
 /* Same launch; additionally CTA (0,0) of the tensor-core kernel writes per-role clock64 counters to dbg[0..15]
@@ -90,6 +98,9 @@ int hd_conv_gemm_profile(const hd_conv_desc *d, void *stream, long long *dbg);
  * [rows, k_pad] of elem_bytes-wide elements (4 = fp32/tf32 path, 2 = fp16 path) with a {128 bytes x box_rows} box and
  * 128-byte swizzle. */
 int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int box_rows, int elem_bytes, void *tmap_out);
+/* Same for a row-major activation matrix [rows, cols] with leading dimension ld_elems (elem_bytes 4 = fp32, 2 = fp16): box
+ * {32 columns x 128 rows}, 128-byte (fp32) / 64-byte (fp16) swizzle -- the slabs of the TMA epilogue. */
+int hd_make_act_tmap(const void *base, long long rows, int cols, long long ld_elems, int elem_bytes, void *tmap_out);
 
 /* ---- ResNet root / tail pieces (slim resnet_v2_50, called from src/models.py:65-74) ---- */
 /* conv1: 7x7 stride 2, explicit zero pad 3+3, + bias.  in [N,H,W,3] -> out [N,H/2,W/2,64]; w [7*7*3,64]. */

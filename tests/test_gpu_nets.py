@@ -121,12 +121,20 @@ def test_conv_gemm_tcgen05_3xf16(case):
     (2, 28, 128, 64, 3, 1, False, False),    # 3x3, split output only, BN=64 tile
     (2, 14, 256, 128, 3, 2, False, False),   # strided 3x3 through the cp.async gather (zero-fill padding)
     (5, 7, 512, 2048, 1, 1, True, True),     # non-DUAL, many N tiles, ragged M (245 rows)
+    (7, 28, 64, 256, 1, 1, True, True),      # K=64: 43 M-tiles x 2 N-tiles on 148 CTAs, ragged last tile (5488 rows)
+    (640, 7, 256, 64, 1, 1, False, False),   # BN=64 tile, 245 tiles > 148 CTAs: several tiles per CTA through the staging ring
+    (9, 14, 128, 512, 1, 1, True, False),    # residual + split output only (no fp32 store)
+    (9, 14, 256, 1024, 1, 1, False, True),   # no residual, both outputs
+    (300, 14, 64, 256, 1, 1, True, True),    # 460 M-tiles x 2: every CTA walks ~6 tiles (ring wrap-around, barrier phases)
 ])
-def test_conv_gemm_presplit_activations(shape):
+@pytest.mark.parametrize('tma', [True, False])
+def test_conv_gemm_presplit_activations(shape, tma, monkeypatch):
     """A operand as a pre-activated fp16 head/remainder pair (cp.async producer) and the epilogue's second output
     relu(v*s2+b2) as such a pair, against an fp64 reference of the same arithmetic."""
     from human_dynamics_b200 import _lib
     from human_dynamics_b200.nets import PackedConv
+    from human_dynamics_b200 import nets
+    monkeypatch.setattr(nets, 'TMA_EPILOGUE', tma)       # K <= 256 layers: TMA-store epilogue vs per-thread epilogue
     n, H, Cin, Cout, k, stride, with_res, fp32_out = shape
     rng = np.random.RandomState(sum(shape))
     dev = torch.device('cuda')
@@ -145,6 +153,7 @@ def test_conv_gemm_presplit_activations(shape):
     op = pc.bind(None, n, H, H, out, inp_split=(hi, lo), out_split=(oh, ol), res=rt,
                  post2=(torch.from_numpy(s2).to(dev), torch.from_numpy(b2).to(dev), 1), impl='tc3h')
     assert op.d.impl == _lib.HD_IMPL_TC_3XF16
+    assert bool(op.d.tmap_out_hi) == (tma and k * k * Cin <= 256), 'TMA epilogue selection'
     op.run(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ac = F.pad(torch.from_numpy(x).double().permute(0, 3, 1, 2), (k // 2,) * 4)
