@@ -90,6 +90,40 @@ __global__ void __launch_bounds__(128) groupnorm_stats_kernel(const float *__res
   }
 }
 
+// process_image (src/evaluation/run_video.py:56-107): one thread per output pixel of the S x S crop.
+//   crop(y,x) = padded_scaled[y0 + y + S][x0 + x + S], padded = edge-replicated => clamp the scaled-image coordinates;
+//   scaled = cv2.resize(2*(u8/255 - 0.5), (Ws,Hs)) bilinear: source coordinate (d + 0.5)*scale - 0.5 computed in double and
+//   narrowed to float like cv2 does, floor, weights (1-f, f), neighbours clamped to the image (cv2's xofs/yofs clipping).
+__global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, int H, int W, const int4 *__restrict__ geom,
+                                     float *__restrict__ out, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * S * S) return;
+  const int x = (int)(i % S);
+  const int y = (int)((i / S) % S);
+  const int n = (int)(i / ((long long)S * S));
+  const int4 g = __ldg(geom + n);              // Hs, Ws, x0, y0
+  const int Hs = g.x, Ws = g.y;
+  const int xs = min(max(g.z + x, 0), Ws - 1), ys = min(max(g.w + y, 0), Hs - 1);
+  const double scale_x = 1.0 / ((double)Ws / (double)W), scale_y = 1.0 / ((double)Hs / (double)H);     // cv2: scale = 1. / inv_scale
+  float fx = (float)((xs + 0.5) * scale_x - 0.5), fy = (float)((ys + 0.5) * scale_y - 0.5);
+  int sx = (int)floorf(fx), sy = (int)floorf(fy);
+  fx -= (float)sx; fy -= (float)sy;
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= W - 1) { fx = 0.f; sx = W - 1; }
+  const int sx1 = min(sx + 1, W - 1);
+  const int sy0 = min(max(sy, 0), H - 1), sy1 = min(max(sy + 1, 0), H - 1);
+  const uint8_t *f = frames + (size_t)n * H * W * 3;
+  const uint8_t *r0 = f + (size_t)sy0 * W * 3, *r1 = f + (size_t)sy1 * W * 3;
+  const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+  float *o = out + (size_t)i * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float p00 = ((float)r0[sx * 3 + c] / 255.f - 0.5f) * 2.f, p01 = ((float)r0[sx1 * 3 + c] / 255.f - 0.5f) * 2.f;
+    const float p10 = ((float)r1[sx * 3 + c] / 255.f - 0.5f) * 2.f, p11 = ((float)r1[sx1 * 3 + c] / 255.f - 0.5f) * 2.f;
+    o[c] = (p00 * a0 + p01 * a1) * b0 + (p10 * a0 + p11 * a1) * b1;
+  }
+}
+
 __global__ void ief_delta_init_kernel(const float *__restrict__ theta, float *__restrict__ dst, int dst_ld, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 85) return;
@@ -151,3 +185,10 @@ int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *s
 }
 
 }  // extern "C"
+
+extern "C" int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *stream) {
+  HD_REQUIRE(frames && geom && out && N > 0 && H > 0 && W > 0 && S > 0 && ((uintptr_t)geom & 15u) == 0, "hd_process_image: bad arguments");
+  const long long total = (long long)N * S * S;
+  process_image_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, N, H, W, reinterpret_cast<const int4 *>(geom), out, S);
+  return hd::check_launch("process_image_kernel");
+}

@@ -17,13 +17,43 @@ from ._lib import current_stream
 
 
 def load_weights(path_or_dict):
-    """TF-named variable dict from an in-memory dict or an .npz (a TF checkpoint must be converted offline)."""
+    """TF-named variable dict from an in-memory dict, an .npz, or a TensorFlow V2 checkpoint prefix
+    (`model.ckpt-NNNN`, recognised like the reference does by its `.index` file, tester.py:35; parsed without TensorFlow
+    by human_dynamics_b200.tf_checkpoint)."""
+    from . import tf_checkpoint
     if isinstance(path_or_dict, dict):
         return path_or_dict
     if isinstance(path_or_dict, str) and path_or_dict.endswith('.npz'):
         with np.load(path_or_dict) as z:
             return {k: z[k] for k in z.files}
-    raise ValueError('weights must be a dict of TF-named arrays or a .npz path (got %r)' % (path_or_dict,))
+    if isinstance(path_or_dict, str) and path_or_dict.endswith('.index') and tf_checkpoint.is_checkpoint(path_or_dict[:-6]):
+        path_or_dict = path_or_dict[:-6]
+    if tf_checkpoint.is_checkpoint(path_or_dict):
+        return tf_checkpoint.load_checkpoint(path_or_dict)
+    raise ValueError('weights must be a dict of TF-named arrays, a .npz path or a TensorFlow checkpoint prefix '
+                     '(got %r; `python tools/ckpt_to_npz.py <prefix> out.npz` converts offline)' % (path_or_dict,))
+
+
+def load_mean_params(path):
+    """`neutral_smpl_meanwjoints.h5` of the reference (tester.py:118-141) -> mean_param (1,85) = [0.9,0,0 | pose with root
+    (pi,0,0) | shape].  Only the INITIAL value of the trainable `mean_param` variable: a restored checkpoint carries the
+    learned one, which wins.  .npz / .npy with 'pose' (72) and 'shape' (10) are read directly; .h5 needs h5py or deepdish
+    (not dependencies of this package)."""
+    if path.endswith('.npz'):
+        with np.load(path) as z:
+            pose, shape = np.array(z['pose'], np.float64), np.array(z['shape'], np.float64)
+    else:
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError('reading %s needs h5py (or convert it once: python -c "import deepdish as dd, numpy as np; '
+                              'v = dd.io.load(PATH); np.savez(OUT, pose=v[\'pose\'], shape=v[\'shape\'])")' % path) from e
+        with h5py.File(path, 'r') as f:
+            pose, shape = np.array(f['pose'], np.float64), np.array(f['shape'], np.float64)
+    pose = pose.reshape(72).copy()
+    pose[:3] = 0.0
+    pose[0] = np.pi                                                            # tester.py:126-127
+    return np.hstack(([0.9, 0.0, 0.0], pose, shape.reshape(10))).astype(np.float32).reshape(1, 85)
 
 
 class PackedHal(object):

@@ -22,13 +22,22 @@ class Tester(object):
         if engine is None and weights is None:
             if not self.load_path:
                 raise Exception('[!] You need to specify `load_path` to load a pretrained model')     # tester.py:31-34
-            if not os.path.exists(self.load_path):
+            if not os.path.exists(self.load_path) and not os.path.exists(self.load_path + '.index'):
                 raise Exception('{} doesnt exist..'.format(self.load_path))                           # tester.py:35-38 (no ipdb)
             weights = load_weights(self.load_path)
         if pretrained_resnet_path:                                                                    # tester.py:99-109
+            if weights is None:
+                raise ValueError('pretrained_resnet_path needs the weights to merge into: pass config.load_path / '
+                                 'config.weights instead of a pre-built engine')
             rw = load_weights(pretrained_resnet_path)
             weights = dict(weights)
             weights.update({k: v for k, v in rw.items() if k.startswith('resnet_v2_50')})
+        if weights is not None and 'mean_param' not in weights:                                       # tester.py:118-141
+            mean_path = os.path.join(os.path.dirname(getattr(config, 'smpl_model_path', '') or ''), 'neutral_smpl_meanwjoints.h5')
+            alt = mean_path[:-3] + '.npz'
+            from human_dynamics_b200.engine import load_mean_params
+            weights = dict(weights)
+            weights['mean_param'] = load_mean_params(alt if os.path.exists(alt) else mean_path)
 
         self.batch_size = config.batch_size
         self.sequence_length = sequence_length if sequence_length else config.sequence_length

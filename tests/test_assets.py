@@ -48,3 +48,123 @@ def test_smpl_pickle_loads_without_chumpy(tmp_path, smpl_model):
     v0 = SMPLRef(smpl_model)(beta, theta, get_skin=True)[0]
     assert np.allclose(v0, v1, atol=1e-6)          # same model through dense vs sparse->dense regressors (BLAS path may differ)
     assert load_smpl_model(smpl_model) is smpl_model
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TensorFlow V2 checkpoint reader (reference: tester.py:92-116 restores `load_path` with tf.train.Saver)
+# ------------------------------------------------------------------------------------------------------------------
+def test_crc32c_known_answers():
+    from human_dynamics_b200.tf_checkpoint import crc32c, mask_crc
+    assert crc32c(b'123456789') == 0xE3069283                # Castagnoli check value (RFC 3720 B.4)
+    assert crc32c(b'\x00' * 32) == 0x8A9136AA                # RFC 3720 B.4: 32 bytes of zeros
+    assert crc32c(b'\xff' * 32) == 0x62A8AB43
+    assert mask_crc(0) == 0xa282ead8
+
+
+def _hand_built_index(tmp_path):
+    """A .index assembled byte by byte from the LevelDB table / tensor-bundle description (independent of save_checkpoint):
+    one data block with the header entry and two variables (second key prefix-compressed against the first)."""
+    import struct
+    from human_dynamics_b200.tf_checkpoint import crc32c, mask_crc
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = np.array([7, -9], dtype=np.int32)
+    raw = a.tobytes() + b.tobytes()
+    prefix = str(tmp_path / 'hand.ckpt-1')
+    open(prefix + '.data-00000-of-00001', 'wb').write(raw)
+
+    def entry(dtype, dims, off, size, crc):
+        shape = b''.join(b'\x12' + bytes([2]) + b'\x08' + bytes([d]) for d in dims)           # Dim{size=d}
+        e = b'\x08' + bytes([dtype]) + b'\x12' + bytes([len(shape)]) + shape
+        if off:
+            e += b'\x20' + bytes([off])
+        return e + b'\x28' + bytes([size]) + b'\x35' + struct.pack('<I', crc)
+    header = b'\x08\x01' + b'\x1a\x02\x08\x01'                                                  # num_shards=1, version{producer=1}
+    ea = entry(1, (2, 3), 0, 24, mask_crc(crc32c(a.tobytes())))
+    eb = entry(3, (2,), 24, 8, mask_crc(crc32c(b.tobytes())))
+    k1, k2 = b'scope/var_a', b'scope/var_b'
+    block = (bytes([0, 0, len(header)]) + header +
+             bytes([0, len(k1), len(ea)]) + k1 + ea +
+             bytes([len(k1) - 1, 1, len(eb)]) + b'b' + eb +                                     # shares 'scope/var_'
+             struct.pack('<II', 0, 1))                                                          # one restart at 0
+    out = bytearray()
+
+    def emit(blk):
+        off = len(out)
+        out.extend(blk + b'\x00' + struct.pack('<I', mask_crc(crc32c(blk + b'\x00'))))
+        return bytes([off]) if off < 128 else bytes([off & 0x7f | 0x80, off >> 7]), bytes([len(blk)])
+    d_off, d_len = emit(block)
+    meta = struct.pack('<II', 0, 1)
+    m_off, m_len = emit(meta)
+    handle = d_off + d_len
+    index = bytes([0, len(k2), len(handle)]) + k2 + handle + struct.pack('<II', 0, 1)
+    i_off, i_len = emit(index)
+    footer = m_off + m_len + i_off + i_len
+    footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', 0xdb4775248b80fb57)
+    out.extend(footer)
+    open(prefix + '.index', 'wb').write(bytes(out))
+    return prefix, a, b
+
+
+def test_checkpoint_reader_on_hand_built_bundle(tmp_path):
+    from human_dynamics_b200 import tf_checkpoint
+    prefix, a, b = _hand_built_index(tmp_path)
+    assert tf_checkpoint.is_checkpoint(prefix)
+    got = tf_checkpoint.load_checkpoint(prefix, verify_data=True)
+    assert sorted(got) == ['scope/var_a', 'scope/var_b']
+    assert got['scope/var_a'].dtype == np.float32 and np.array_equal(got['scope/var_a'], a)
+    assert got['scope/var_b'].dtype == np.int32 and np.array_equal(got['scope/var_b'], b)
+    # corruption is detected: flip one byte of the data block
+    raw = bytearray(open(prefix + '.index', 'rb').read())
+    raw[10] ^= 0x40
+    open(prefix + '.index', 'wb').write(bytes(raw))
+    import pytest
+    with pytest.raises(ValueError):
+        tf_checkpoint.read_index(prefix + '.index')
+
+
+def test_checkpoint_roundtrip_full_weight_set(tmp_path, weights):
+    """All ~300 TF-named variables of the path through writer -> reader (many data blocks, prefix compression, restarts),
+    optimizer slots / discriminator variables dropped like tester.py:163-167, then through engine.load_weights."""
+    from human_dynamics_b200 import tf_checkpoint
+    from human_dynamics_b200.engine import load_weights
+    small = {k: v for k, v in weights.items() if v.size <= 4096 or k.endswith('mean_param')}
+    small['D_fc1/weights'] = np.ones((3, 3), np.float32)
+    small['single_view_ief/3D_module/fc3/biases/Adam'] = np.zeros(85, np.float32)
+    small['global_step'] = np.array(1119816, np.int64)
+    prefix = str(tmp_path / 'hmmr_model.ckpt-1119816')
+    tf_checkpoint.save_checkpoint(prefix, small, block_size=512)
+    nshards, entries = tf_checkpoint.read_index(prefix + '.index')
+    assert nshards == 1 and set(entries) == set(small)
+    got = load_weights(prefix)                               # prefix, the way config.load_path names it
+    assert set(got) == {k for k in small if not (k.startswith('D_') or k.endswith('/Adam') or k == 'global_step')}
+    for k, v in got.items():
+        assert v.dtype == small[k].dtype and v.shape == small[k].shape and np.array_equal(v, small[k]), k
+    assert set(load_weights(prefix + '.index')) == set(got)
+    only = tf_checkpoint.load_checkpoint(prefix, names=['global_step'], verify_data=True)
+    assert int(np.asarray(only['global_step']).reshape(-1)[0]) == 1119816
+
+
+def test_mean_param_loader(tmp_path):
+    from human_dynamics_b200.engine import load_mean_params
+    rng = np.random.RandomState(0)
+    pose, shape = rng.normal(size=72), rng.normal(size=10)
+    p = str(tmp_path / 'neutral_smpl_meanwjoints.npz')
+    np.savez(p, pose=pose, shape=shape)
+    m = load_mean_params(p)
+    assert m.shape == (1, 85) and m.dtype == np.float32
+    assert np.allclose(m[0, :3], [0.9, 0, 0]) and np.allclose(m[0, 3:6], [np.pi, 0, 0])      # tester.py:124-127
+    assert np.allclose(m[0, 6:75], pose[3:], atol=1e-6) and np.allclose(m[0, 75:], shape, atol=1e-6)
+
+
+def test_smpl_faces_fixture_is_bit_exact():
+    """north_star: bit-exact face indexing.  The table ships with the drop-in package exactly as the reference ships it
+    (src/tf_smpl/smpl_faces.npy, consumed by the renderer at src/util/render/nmr_renderer.py:54,63)."""
+    import hashlib
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'src', 'tf_smpl', 'smpl_faces.npy')
+    data = open(path, 'rb').read()
+    assert len(data) == 165392
+    assert hashlib.sha256(data).hexdigest().startswith('51fc11eb') and hashlib.sha256(data).hexdigest().endswith('859fecb')
+    f = np.load(path)
+    assert f.shape == (13776, 3) and f.dtype == np.uint32 and f.min() == 0 and f.max() == 6889
+    assert len(np.unique(f)) == 6890

@@ -1,0 +1,97 @@
+"""process_image (src/evaluation/run_video.py:56-107): host geometry on CPU, the CUDA crop kernel on the GPU, both against
+the cv2 restatement (oracle/preproc_ref.py) and the committed golden fixture."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden', 'process_image_golden_v1.npz')
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location('make_preproc_golden', os.path.join(ROOT, 'tests', 'golden', 'make_preproc_golden.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_oracle_reproduces_golden_fixture():
+    cv2 = pytest.importorskip('cv2')
+    from oracle import preproc_ref
+    gen = _gen()
+    with np.load(GOLD) as z:
+        for i, (H, W, cx, cy, s) in enumerate(z['cases']):
+            r = preproc_ref.process_image(gen.frame(i, int(H), int(W)), [cx, cy, s])
+            assert np.allclose(r['image'][::7, ::7], z['img_%d' % i], atol=1e-6)
+            assert list(r['center']) + list(r['start_pt']) + list(r['im_shape']) == list(z['meta_%d' % i])
+
+
+def test_crop_geometry_matches_reference_bookkeeping():
+    """center / start_pt / im_shape (run_video.py:75-100) for the golden cases and a random sweep."""
+    pytest.importorskip('cv2')
+    from oracle import preproc_ref
+    from human_dynamics_b200.preprocess import crop_geometry
+    gen = _gen()
+    with np.load(GOLD) as z:
+        for i, (H, W, cx, cy, s) in enumerate(z['cases']):
+            g = crop_geometry((int(H), int(W)), [cx, cy, s])
+            assert list(g['center']) + list(g['start_pt']) + list(g['im_shape']) == list(z['meta_%d' % i])
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        H, W = int(rng.randint(60, 400)), int(rng.randint(60, 400))
+        s = float(rng.uniform(0.3, 2.0))
+        cx, cy = float(rng.uniform(0, W)), float(rng.uniform(0, H))
+        r = preproc_ref.process_image(np.zeros((H, W, 3), np.uint8), [cx, cy, s])
+        g = crop_geometry((H, W), [cx, cy, s])
+        assert list(g['center']) == list(r['center']) and list(g['start_pt']) == list(r['start_pt'])
+        assert g['im_shape'] == r['im_shape'] == [224, 224]
+    with pytest.raises(ValueError):
+        crop_geometry((100, 100), [900.0, 50.0, 1.0])          # more than one crop away: the reference returns a ragged crop
+
+
+@pytest.mark.gpu
+def test_process_images_kernel_matches_cv2_restatement():
+    pytest.importorskip('cv2')
+    import torch
+    from oracle import preproc_ref
+    from human_dynamics_b200.preprocess import process_images
+    gen = _gen()
+    with np.load(GOLD) as z:
+        for i, (H, W, cx, cy, s) in enumerate(z['cases']):
+            f = gen.frame(i, int(H), int(W))
+            crops, geoms = process_images(f[None], [[cx, cy, s]])
+            got = crops[0].cpu().numpy()
+            assert np.abs(got[::7, ::7] - z['img_%d' % i]).max() < 2e-6, i                  # committed fixture
+            ref = preproc_ref.process_image(f, [cx, cy, s])
+            assert np.abs(got - ref['image']).max() < 2e-6, i                                # every pixel, live cv2
+            assert list(geoms[0]['center']) == list(ref['center'])
+    # a batch of same-size frames with different boxes (the video case), random sweep incl. heavy down / up scaling
+    rng = np.random.RandomState(5)
+    H, W, N = 270, 480, 12
+    frames = np.stack([gen.frame(20 + i, H, W) for i in range(N)])
+    boxes = np.stack([rng.uniform(0, W, N), rng.uniform(0, H, N), rng.uniform(0.35, 2.2, N)], axis=1)
+    crops, _ = process_images(torch.from_numpy(frames), boxes)
+    got = crops.cpu().numpy()
+    for i in range(N):
+        ref = preproc_ref.process_image(frames[i], boxes[i])
+        assert np.abs(got[i] - ref['image']).max() < 2e-6, i
+    assert got.min() >= -1.0 and got.max() <= 1.0
+
+
+@pytest.mark.gpu
+def test_run_video_process_image_surface():
+    """src.evaluation.run_video.process_image: same dict as the reference (run_video.py:99-107)."""
+    pytest.importorskip('cv2')
+    from oracle import preproc_ref
+    from src.evaluation.run_video import process_image
+    gen = _gen()
+    f = gen.frame(3, 200, 300)
+    got = process_image(f, np.array([150.2, 90.9, 0.8]))
+    ref = preproc_ref.process_image(f, [150.2, 90.9, 0.8])
+    assert set(got) == {'image', 'im_path', 'im_shape', 'center', 'scale', 'start_pt'}
+    assert got['image'].shape == (224, 224, 3) and got['image'].dtype == np.float32
+    assert np.abs(got['image'] - ref['image']).max() < 2e-6
+    assert list(got['center']) == list(ref['center']) and list(got['start_pt']) == list(ref['start_pt'])
+    assert got['im_shape'] == ref['im_shape'] and got['scale'] == ref['scale']
