@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libhd_b200.so')
 
 HD_IMPL_SIMT, HD_IMPL_TC_3XTF32, HD_IMPL_TC_1XTF32, HD_IMPL_TC_3XF16 = 0, 1, 2, 3
 HD_CONV_NO_TMA_EPILOGUE = 1
+HD_CONV_INPUT_PLANES = 2
 IMPL_BY_NAME = {'simt': HD_IMPL_SIMT, 'tc3': HD_IMPL_TC_3XTF32, 'tc1': HD_IMPL_TC_1XTF32, 'tc3h': HD_IMPL_TC_3XF16}
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     'hd_conv_gemm_profile': (_i, [C.POINTER(ConvDesc), _vp, _vp]),
     'hd_make_weight_tmap': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'hd_make_act_tmap': (_i, [_vp, _ll, _i, _ll, _i, _vp]),
+    'hd_pack_conv1_planes': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -18,6 +18,7 @@ struct ConvParams {
   const void *in_hi, *in_lo;      // pre-split fp16 activations (cp.async producer) or nullptr
   void *out_hi, *out_lo; long long out2_ld;
   const float *post2_scale, *post2_shift; int post2_relu;
+  int planes;      // A operand = padded RGBX fp16 planes of the resnet conv1 input (see conv_tc.cu producer)
   long long *dbg;  // optional: per-role cycle counters of CTA (0,0) (hd_conv_gemm_profile), else nullptr
 };
 
@@ -74,6 +75,7 @@ inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
               (!d->res || ((d->res_ld % 4 == 0) && aligned16(d->res))) &&
               (!d->post_scale || aligned16(d->post_scale)) && (!d->post_shift || aligned16(d->post_shift));
   p.K_pad = d->K_pad;
+  p.planes = (d->flags & HD_CONV_INPUT_PLANES) ? 1 : 0;
   p.dbg = nullptr;
   return HD_OK;
 }

@@ -273,13 +273,18 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (prof) t_wait += clock64() - tw0;
         const int kb = kc * BKE;
-        const int tap = kb / p.Cin, ci = kb - tap * p.Cin + j * 8;
+        // planes (resnet conv1 over the padded RGBX fp16 planes, Cin = 32 halves = one kernel row of 7(+1) pixels x 4): a 64-wide
+        // chunk holds TWO kernel rows; this thread's 16-byte piece is pixels 2*(j&3), 2*(j&3)+1 of row ky.  KH = 8: row 7 is a
+        // phantom (zero weights) and is zero-filled.
+        const int tap = p.planes ? 2 * kc + (j >> 2) : kb / p.Cin;
+        const int ci = p.planes ? (j & 3) * 8 : kb - tap * p.Cin + j * 8;
         const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        const bool tap_ok = !p.planes || tap < 7;
         const uint32_t a_hi = smem_base + s * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int iy = rs.iy[i] + ky, ix = rs.ix[i] + kx;
-          const bool ok = rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const bool ok = tap_ok && rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
           const size_t e = ok ? ((size_t)((size_t)rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci : 0;
           const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
           cp_async16(a_hi + off, ihi + e, ok ? 16u : 0u);
@@ -896,6 +901,16 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
   if ((p.out_hi || p.in_hi) && (!half || !p.vec_out)) {
     set_last_error_text("hd_conv_gemm(tc): pre-split activations need impl 3 and 16-byte aligned, 4-column-multiple outputs");
     return HD_ERR_INVALID;
+  }
+  if (p.in_hi && p.planes) {           // resnet conv1 over padded RGBX fp16 planes (hd_pack_conv1_planes)
+    if (p.Cin != 32 || p.KH != 8 || p.KW != 1 || p.stride != 2 || p.pad_t != 0 || p.pad_l != 0 || p.in_ld != 4 || p.Cout > 64 ||
+        p.W % 2 != 0 || 2 * (p.Wo - 1) + 8 > p.W || 2 * (p.Ho - 1) + 7 > p.H || !aligned16(p.in_hi) || !aligned16(p.in_lo) || p.pre_scale) {
+      set_last_error_text("hd_conv_gemm(tc planes): needs the conv1 plane geometry (Cin 32, KH 8, KW 1, stride 2, in_ld 4, even W)");
+      return HD_ERR_INVALID;
+    }
+    const bool maps = p.out && d->tmap_out && !p.res && !p.out_hi;
+    if (maps && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE)) return launch_tc<64, true, 4, true, false, true, false, true>(p, d, st);
+    return launch_tc<64, true, 4, true, false, true, true>(p, d, st);
   }
   if (p.in_hi) {                       // pre-split fp16 activations: cp.async producer
     if (p.Cin % 64 != 0 || p.K % 64 != 0 || p.in_ld % 8 != 0 || !aligned16(p.in_hi) || !aligned16(p.in_lo) || p.pre_scale) {

@@ -124,6 +124,23 @@ __global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, 
   }
 }
 
+// fp32 NHWC image -> padded RGBX fp16 head / remainder planes (the A operand of the tensor-core conv1).  One thread per pixel.
+__global__ void pack_conv1_planes_kernel(const float *__restrict__ img, uint2 *__restrict__ hi, uint2 *__restrict__ lo, int N, int H, int W,
+                                         int WP) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int n = (int)(i / ((long long)W * H));
+  const float *s = img + (size_t)i * 3;
+  uint32_t h0, l0, h1, l1;
+  hd::split_f16x2(__ldg(s), __ldg(s + 1), h0, l0);
+  hd::split_f16x2(__ldg(s + 2), 0.f, h1, l1);
+  const size_t o = ((size_t)n * (H + 6) + y + 3) * WP + x + 3;
+  hi[o] = make_uint2(h0, h1);
+  lo[o] = make_uint2(l0, l1);
+}
+
 __global__ void ief_delta_init_kernel(const float *__restrict__ theta, float *__restrict__ dst, int dst_ld, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 85) return;
@@ -191,4 +208,14 @@ extern "C" int hd_process_image(const unsigned char *frames, int N, int H, int W
   const long long total = (long long)N * S * S;
   process_image_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, N, H, W, reinterpret_cast<const int4 *>(geom), out, S);
   return hd::check_launch("process_image_kernel");
+}
+
+extern "C" int hd_pack_conv1_planes(const float *img, void *plane_hi, void *plane_lo, int N, int H, int W, int WP, void *stream) {
+  HD_REQUIRE(img && plane_hi && plane_lo && N > 0 && H > 0 && W > 0 && WP >= W + 8 && WP % 2 == 0 && hd::aligned16(plane_hi) &&
+                 hd::aligned16(plane_lo),
+             "hd_pack_conv1_planes: bad arguments");
+  const long long total = (long long)N * H * W;
+  pack_conv1_planes_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<uint2 *>(plane_hi),
+                                                                                     reinterpret_cast<uint2 *>(plane_lo), N, H, W, WP);
+  return hd::check_launch("pack_conv1_planes_kernel");
 }

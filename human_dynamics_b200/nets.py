@@ -229,6 +229,60 @@ class ConvOp(object):
             check(rc, 'hd_conv_gemm')
 
 
+CONV1_PLANES = os.environ.get('HD_CONV1_PLANES', '1') != '0'      # A/B switch: conv1 from padded fp16 planes vs fp32 row-segment gather
+
+
+class PackedConv1Planes(object):
+    """ResNet root conv1 (7x7 stride 2, explicit pad 3+3, bias; A.2) on the tensor cores, reading its input as two padded
+    RGBX fp16 planes [n, S+6, WP, 4] (head / remainder, hd_pack_conv1_planes): every (output pixel, kernel row) needs 8
+    consecutive pixels = 64 contiguous, 16-byte-aligned bytes per plane, which four cp.async move straight into the swizzled
+    A tile.  GEMM view: K = 8 kernel rows x 8 pixels x 4 channels = 256 (the 8th row / pixel / channel carry zero weights)."""
+
+    def __init__(self, w_hwio, bias, device):
+        w = np.asarray(w_hwio, np.float32)
+        assert w.shape == (7, 7, 3, 64), w.shape
+        self.device = device
+        self.Cout, self.K = 64, 256
+        w_nk = np.zeros((64, 8, 8, 4), np.float32)                 # [co, ky, kx, c]
+        w_nk[:, :7, :7, :3] = w.transpose(3, 0, 1, 2)
+        hi, lo = f16_split(w_nk.reshape(64, 256))
+        self.w_nk_hi = torch.from_numpy(hi).to(device)
+        self.w_nk_lo = torch.from_numpy(lo).to(device)
+        self.bias = _dev(bias, device)
+        self.tmap_hi = (C.c_ubyte * 128)()
+        self.tmap_lo = (C.c_ubyte * 128)()
+        for t, m in ((self.w_nk_hi, self.tmap_hi), (self.w_nk_lo, self.tmap_lo)):
+            check(lib.hd_make_weight_tmap(C.c_void_p(t.data_ptr()), 64, 256, 64, 2, C.cast(m, C.c_void_p)), 'hd_make_weight_tmap')
+
+    @staticmethod
+    def plane_width(size):
+        return (size + 8 + 1) // 2 * 2
+
+    def alloc_planes(self, n, size):
+        """Zero-initialised planes: the 3-pixel border (and the spare columns) must be zero and is never written again."""
+        shape = (n, size + 6, self.plane_width(size), 4)
+        return (torch.zeros(shape, dtype=torch.float16, device=self.device), torch.zeros(shape, dtype=torch.float16, device=self.device))
+
+    def bind(self, planes, n, size, out):
+        d = ConvDesc()
+        WP = self.plane_width(size)
+        d.in_hi, d.in_lo = planes[0].data_ptr(), planes[1].data_ptr()
+        d.in_ld = 4
+        d.n_img, d.H, d.W, d.Cin = n, size + 6, WP, 32
+        d.Ho = d.Wo = size // 2
+        d.KH, d.KW, d.stride, d.pad_t, d.pad_l = 8, 1, 2, 0, 0
+        d.Cout, d.K_pad = 64, 256
+        d.post_shift = self.bias.data_ptr()
+        d.out, d.out_ld = out.data_ptr(), 64
+        d.impl = _lib.HD_IMPL_TC_3XF16
+        d.w_nk_hi, d.w_nk_lo = self.w_nk_hi.data_ptr(), self.w_nk_lo.data_ptr()
+        d.tmap_hi, d.tmap_lo = C.cast(self.tmap_hi, C.c_void_p), C.cast(self.tmap_lo, C.c_void_p)
+        d.flags = _lib.HD_CONV_INPUT_PLANES | (0 if TMA_EPILOGUE else _lib.HD_CONV_NO_TMA_EPILOGUE)
+        op = ConvOp(d, (self, planes, out), (size // 2, size // 2))
+        op.encode_act_maps()
+        return op
+
+
 # ------------------------------------------------------------------------------------------------
 # ResNet-v2-50 (slim)  -- src/models.py:50-77
 # ------------------------------------------------------------------------------------------------
@@ -241,6 +295,8 @@ class PackedResNet(object):
         self.conv1_b = _dev(w[p + '/conv1/biases'], device)
         # conv2d_same(7x7, stride 2): explicit pad 3+3 then VALID (A.2); tensor-core path gathers the ragged K=147 element-wise
         self.conv1 = PackedConv(w[p + '/conv1/weights'], device, post_shift=w[p + '/conv1/biases'], stride=2, pad=(3, 3), tc=tc)
+        want = {True: 'f16', 'auto': 'f16', 'tc3h': 'f16'}.get(tc, None)
+        self.conv1_planes = PackedConv1Planes(w[p + '/conv1/weights'], w[p + '/conv1/biases'], device) if want == 'f16' else None
         self.units = []
         d_in = 64
         for b, (base, units, bstride) in enumerate(blocks, start=1):
@@ -313,7 +369,11 @@ class ResNetPlan(object):
         self.bufS = torch.empty(n * mx_io, **f32)
         self.ops = []
         self.conv1_op = None
-        if root and packed.conv1.tc and impl != 'simt':
+        self.planes = None
+        if root and packed.conv1_planes is not None and impl in ('auto', 'tc3h') and CONV1_PLANES and size % 2 == 0:
+            self.planes = packed.conv1_planes.alloc_planes(n, size)
+            self.conv1_op = packed.conv1_planes.bind(self.planes, n, size, self.bufS)
+        elif root and packed.conv1.tc and impl != 'simt':
             self.conv1_op = packed.conv1.bind(self.bufS, n, size, size, self.bufS, in_ld=3, impl=impl)   # `in_` is set per run
         self.in_refs = []                     # (op, field) descriptor fields that read the stage input
         self.pool_split = None
@@ -414,7 +474,12 @@ class ResNetPlan(object):
         st = current_stream() if stream is None else stream
         n, p = self.n, self.p
         if self.root:
-            if self.conv1_op is not None:
+            if self.planes is not None:
+                if images is not None:        # None: the planes were filled by the caller (uint8 frames through hd_process_image_planes)
+                    check(lib.hd_pack_conv1_planes(fptr(images), C.c_void_p(self.planes[0].data_ptr()), C.c_void_p(self.planes[1].data_ptr()),
+                                                   n, self.size, self.size, self.planes[0].shape[2], st), 'hd_pack_conv1_planes')
+                self.conv1_op.run(st)
+            elif self.conv1_op is not None:
                 self.conv1_op.d.in_ = images.data_ptr()
                 self.conv1_op.run(st)
             else:
@@ -433,7 +498,7 @@ class ResNetPlan(object):
 
     @property
     def num_launches(self):
-        return (2 if self.root else 0) + len(self.ops) + (1 if self.tail else 0)
+        return ((3 if self.planes is not None else 2) if self.root else 0) + len(self.ops) + (1 if self.tail else 0)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -87,7 +87,13 @@ typedef struct {
   int flags;
 } hd_conv_desc;
 
-enum { HD_CONV_NO_TMA_EPILOGUE = 1 };
+enum {
+  HD_CONV_NO_TMA_EPILOGUE = 1,
+  /* in_hi / in_lo are the padded RGBX fp16 planes written by hd_pack_conv1_planes / hd_process_image_planes: the 7x7 stride-2
+   * conv1 of the ResNet root is then described as Cin = 32 (one kernel row = 8 pixels x 4 channels, 7 real + 1 zero-weight),
+   * KH = 8 (7 real + 1 zero-weight), KW = 1, stride = 2, pad = 0, H = Hi + 6, W = even(Wi + 8), in_ld = 4, K = 256. */
+  HD_CONV_INPUT_PLANES = 2
+};
 
 int hd_conv_gemm(const hd_conv_desc *d, void *stream);
 /* Same launch; additionally CTA (0,0) of the tensor-core kernel writes per-role clock64 counters to dbg[0..15]
@@ -103,6 +109,10 @@ int hd_make_weight_tmap(const void *w_nk, int rows, int k_pad, int box_rows, int
 int hd_make_act_tmap(const void *base, long long rows, int cols, long long ld_elems, int elem_bytes, void *tmap_out);
 
 /* ---- ResNet root / tail pieces (slim resnet_v2_50, called from src/models.py:65-74) ---- */
+/* Input of the tensor-core conv1 (HD_CONV_INPUT_PLANES): img fp32 [N,H,W,3] -> two fp16 planes [N, H+6, WP, 4] (head and
+ * 2^11-scaled remainder of every sample, channel 3 = 0), the image at row/column offset 3 inside a zero border that the
+ * caller clears ONCE (the kernel writes the interior only).  WP = plane row length in pixels (even, >= W + 8). */
+int hd_pack_conv1_planes(const float *img, void *plane_hi, void *plane_lo, int N, int H, int W, int WP, void *stream);
 /* conv1: 7x7 stride 2, explicit zero pad 3+3, + bias.  in [N,H,W,3] -> out [N,H/2,W/2,64]; w [7*7*3,64]. */
 int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *out, int N, int H, int W, void *stream);
 /* pool1: 3x3 stride 2 max pool, TF SAME padding (pad 0 top/left, 1 bottom/right for even sizes).

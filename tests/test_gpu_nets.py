@@ -335,3 +335,39 @@ def test_hal_mode_and_models_surface(weights, smpl_model):
     v_ref, _, _ = SMPLRef(smpl_model)(raw[:, 75:], raw[:, 3:75], get_skin=True)
     assert rel_err(op.get_verts().cpu().numpy().reshape(v_ref.shape), v_ref) < REL
     assert op.get_kps().shape == (B, T, 25, 2) and op.get_poses_rot().shape == (B, T, 24, 3, 3)
+
+
+@pytest.mark.parametrize('n,size', [(2, 24), (3, 224), (5, 64)])
+@pytest.mark.parametrize('tma', [True, False])
+def test_conv1_from_padded_fp16_planes(n, size, tma, monkeypatch):
+    """ResNet root conv1 (7x7/2, explicit pad 3+3, bias) through the plane-input tensor-core path: hd_pack_conv1_planes
+    + hd_conv_gemm(HD_CONV_INPUT_PLANES) against an fp64 convolution."""
+    from human_dynamics_b200 import nets
+    from human_dynamics_b200._lib import lib, check, fptr
+    import ctypes as C
+    monkeypatch.setattr(nets, 'TMA_EPILOGUE', tma)
+    rng = np.random.RandomState(n * 1000 + size)
+    dev = torch.device('cuda')
+    x = rng.uniform(-1, 1, size=(n, size, size, 3)).astype(np.float32)
+    w = (rng.normal(0, 1, size=(7, 7, 3, 64)) / np.sqrt(147)).astype(np.float32)
+    b = rng.normal(0, 0.2, size=64).astype(np.float32)
+    pc = nets.PackedConv1Planes(w, b, dev)
+    planes = pc.alloc_planes(n, size)
+    out = torch.zeros((n, size // 2, size // 2, 64), device=dev)
+    op = pc.bind(planes, n, size, out)
+    assert bool(op.d.tmap_out) == tma
+    st = torch.cuda.current_stream().cuda_stream
+    xt = torch.from_numpy(x).to(dev)
+    for _ in range(2):          # twice: the zero border must survive the first pass
+        check(lib.hd_pack_conv1_planes(fptr(xt), C.c_void_p(planes[0].data_ptr()), C.c_void_p(planes[1].data_ptr()), n, size, size,
+                                       planes[0].shape[2], st), 'pack')
+        op.run(st)
+    torch.cuda.synchronize()
+    ac = F.pad(torch.from_numpy(x).double().permute(0, 3, 1, 2), (3, 3, 3, 3))
+    y = F.conv2d(ac, torch.from_numpy(w).double().permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1) + torch.from_numpy(b).double()
+    assert tuple(out.shape) == tuple(y.shape)
+    assert rel_err(out.cpu().numpy(), y.numpy()) < 2e-5
+    # the planes represent the image to ~2^-22 and keep a zero border
+    rec = planes[0].float() + planes[1].float() / 2048.0
+    assert float((rec[:, 3:3 + size, 3:3 + size, :3] - xt).abs().max()) < 1e-6
+    assert float(rec[:, :3].abs().max()) == 0 and float(rec[:, :, :3].abs().max()) == 0 and float(rec[..., 3].abs().max()) == 0
