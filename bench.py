@@ -168,6 +168,8 @@ def main():
     ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '160')))
     ap.add_argument('--late-chunk', type=int, default=int(os.environ.get('HD_LATE_CHUNK', '640')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', type=int, default=int(os.environ.get('HD_GRAPH', '1')),
+                    help='1 = replay the device-resident step from a CUDA graph (one graph launch per step), 0 = eager launches')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
@@ -239,7 +241,10 @@ def main():
         last = {}
 
         def step():
-            out = eng.predict(img_dev, single_frame=single)
+            if args.graph:
+                out, last['nodes'] = eng.predict_graphed(img_dev, single_frame=single)
+            else:
+                out = eng.predict(img_dev, single_frame=single)
             last['out'] = out
             if world > 1:
                 last['g'] = gather_outputs({k: out[k] for k in gather_keys}, B * world, dst=0)
@@ -266,6 +271,10 @@ def main():
     barrier()
     t_end = sampler.mark()
     launches = int(_lib.lib.hd_launch_count())
+    graph_nodes = None
+    if args.workload != 'smpl' and args.graph and last.get('nodes'):
+        graph_nodes = int(last['nodes'])
+        launches = graph_nodes * args.steps          # kernels executed inside the timed region (submitted as `steps` graph launches)
     clocks = sampler.stop(t_begin, t_end)
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:
@@ -341,6 +350,8 @@ def main():
                            'peaks': peaks['source']},
                 'clocks': clocks, 'gpu_launches': launches,
                 'gpu_launches_per_step': launches / max(1, args.steps)}
+        if graph_nodes:
+            line['cuda_graph'] = {'graph_launches_per_step': 1, 'kernel_nodes_per_graph': graph_nodes}
         if e2e:
             line['e2e'] = e2e
         if roofline:

@@ -202,3 +202,29 @@ def test_fp16_split_saturates_instead_of_nan():
     assert torch.isfinite(out).all() and float(out.min()) > 65504
     assert torch.isfinite(oh).all() and torch.isfinite(ol).all()
     assert float(oh.float().min()) == 65504.0 and float(ol.float().abs().max()) == 0.0
+
+
+def test_cuda_graph_replay_equals_eager(weights, smpl_model):
+    """predict_graphed: one graph launch per window; results bit-identical to the eager launches, and new frames written
+    into the same input buffer are picked up by the replay."""
+    from human_dynamics_b200 import synthetic, HMMRConfig, _lib
+    from human_dynamics_b200.engine import HMMREngine
+    B, T, S = 2, 20, 64
+    eng = HMMREngine(weights, smpl_model, HMMRConfig(batch_size=B, sequence_length=T, img_size=S))
+    a = torch.from_numpy(synthetic.make_images(B * T, seed=1, size=S)).cuda().view(B, T, S, S, 3)
+    b = torch.from_numpy(synthetic.make_images(B * T, seed=2, size=S)).cuda().view(B, T, S, S, 3)
+    buf = a.clone()
+    eager_a = {k: v.clone() for k, v in eng.predict(a).items() if not k.startswith('_')}
+    eager_b = {k: v.clone() for k, v in eng.predict(b).items() if not k.startswith('_')}
+    out, nodes = eng.predict_graphed(buf)
+    torch.cuda.synchronize()
+    assert nodes > 100
+    for k in eager_a:
+        assert torch.equal(out[k], eager_a[k]), k
+    buf.copy_(b)
+    _lib.lib.hd_launch_count_reset()
+    out, _ = eng.predict_graphed(buf)
+    torch.cuda.synchronize()
+    assert _lib.lib.hd_launch_count() == 0          # nothing was launched from the host: the graph did it
+    for k in eager_b:
+        assert torch.equal(out[k], eager_b[k]), k
