@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) groupnorm_stats_kernel(const float *__res
 //   scaled = cv2.resize(2*(u8/255 - 0.5), (Ws,Hs)) bilinear: source coordinate (d + 0.5)*scale - 0.5 computed in double and
 //   narrowed to float like cv2 does, floor, weights (1-f, f), neighbours clamped to the image (cv2's xofs/yofs clipping).
 __global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, int H, int W, const int4 *__restrict__ geom,
-                                     float *__restrict__ out, int S) {
+                                     float *__restrict__ out, int S, uint2 *__restrict__ plane_hi, uint2 *__restrict__ plane_lo, int WP) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * S * S) return;
   const int x = (int)(i % S);
@@ -115,12 +115,24 @@ __global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, 
   const uint8_t *f = frames + (size_t)n * H * W * 3;
   const uint8_t *r0 = f + (size_t)sy0 * W * 3, *r1 = f + (size_t)sy1 * W * 3;
   const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-  float *o = out + (size_t)i * 3;
+  float v[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float p00 = ((float)r0[sx * 3 + c] / 255.f - 0.5f) * 2.f, p01 = ((float)r0[sx1 * 3 + c] / 255.f - 0.5f) * 2.f;
     const float p10 = ((float)r1[sx * 3 + c] / 255.f - 0.5f) * 2.f, p11 = ((float)r1[sx1 * 3 + c] / 255.f - 0.5f) * 2.f;
-    o[c] = (p00 * a0 + p01 * a1) * b0 + (p10 * a0 + p11 * a1) * b1;
+    v[c] = (p00 * a0 + p01 * a1) * b0 + (p10 * a0 + p11 * a1) * b1;
+  }
+  if (out) {
+    float *o = out + (size_t)i * 3;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+  }
+  if (plane_hi) {        // the tensor-core conv1's input format (see pack_conv1_planes_kernel): the fp32 crop need not exist at all
+    uint32_t h0, l0, h1, l1;
+    hd::split_f16x2(v[0], v[1], h0, l0);
+    hd::split_f16x2(v[2], 0.f, h1, l1);
+    const size_t po = ((size_t)n * (S + 6) + y + 3) * WP + x + 3;
+    plane_hi[po] = make_uint2(h0, h1);
+    plane_lo[po] = make_uint2(l0, l1);
   }
 }
 
@@ -203,10 +215,15 @@ int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *s
 
 }  // extern "C"
 
-extern "C" int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *stream) {
-  HD_REQUIRE(frames && geom && out && N > 0 && H > 0 && W > 0 && S > 0 && ((uintptr_t)geom & 15u) == 0, "hd_process_image: bad arguments");
+extern "C" int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *plane_hi,
+                                void *plane_lo, int WP, void *stream) {
+  HD_REQUIRE(frames && geom && (out || plane_hi) && N > 0 && H > 0 && W > 0 && S > 0 && ((uintptr_t)geom & 15u) == 0 &&
+                 ((plane_hi == nullptr) == (plane_lo == nullptr)) && (!plane_hi || (WP >= S + 8 && WP % 2 == 0 && hd::aligned16(plane_hi) && hd::aligned16(plane_lo))),
+             "hd_process_image: bad arguments");
   const long long total = (long long)N * S * S;
-  process_image_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, N, H, W, reinterpret_cast<const int4 *>(geom), out, S);
+  process_image_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, N, H, W, reinterpret_cast<const int4 *>(geom), out, S,
+                                                                                 reinterpret_cast<uint2 *>(plane_hi),
+                                                                                 reinterpret_cast<uint2 *>(plane_lo), WP);
   return hd::check_launch("process_image_kernel");
 }
 

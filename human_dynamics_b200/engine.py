@@ -6,6 +6,8 @@ streams and host<->device copies only.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -123,11 +125,16 @@ class HMMREngine(object):
             i += n
         return out
 
-    def _trunk(self, images, phi, events=None):
+    def _trunk(self, images, phi, events=None, frames=None):
         """ResNet over N frames in two stages: root + blocks 1-2 per `frame_chunk` frames (working set near L2),
         then blocks 3-4 + postnorm/mean per `late_chunk` frames (small maps need many frames to fill the SMs).
-        `events[i]` (optional) is waited on before chunk i of stage A (host->device copy of that chunk)."""
-        N, size = images.shape[0], images.shape[1]
+        `events[i]` (optional) is waited on before chunk i of stage A (host->device copy of that chunk).
+        `frames` = (uint8 [N,H,W,3] CUDA tensor, int32 [N,4] geometry table): stage A then starts from raw video frames --
+        process_image (run_video.py:56-107) writes conv1's input planes directly and `images` is unused (None)."""
+        if frames is not None:
+            N, size = frames[0].shape[0], int(self.config.img_size)
+        else:
+            N, size = images.shape[0], images.shape[1]
         st = current_stream()
         cA = max(1, min(int(self.config.frame_chunk), N))
         cB = max(1, min(int(self.config.late_chunk), N))
@@ -150,7 +157,24 @@ class HMMREngine(object):
                 for ev in events[i // self.H2D_PIECE:(i + n + self.H2D_PIECE - 1) // self.H2D_PIECE]:
                     main.wait_event(ev)
             plan.set_output(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
-            plan.run(images[i:i + n], None, st)
+            if frames is None:
+                plan.run(images[i:i + n], None, st)
+            else:
+                fr, geom = frames
+                H, W = fr.shape[1], fr.shape[2]
+                if plan.planes is not None:
+                    _lib.check(_lib.lib.hd_process_image(C.c_void_p(fr[i:i + n].data_ptr()), n, H, W, C.c_void_p(geom[i:i + n].data_ptr()), None,
+                                                         size, C.c_void_p(plan.planes[0].data_ptr()), C.c_void_p(plan.planes[1].data_ptr()),
+                                                         plan.planes[0].shape[2], st), 'hd_process_image')
+                    plan.run(None, None, st)
+                else:                                 # conv1 without the plane path (simt / tc3 modes): materialise the fp32 crops
+                    ckey = ('crops', n, size)
+                    if ckey not in self._phi:
+                        self._phi[ckey] = torch.empty((n, size, size, 3), dtype=torch.float32, device=self.device)
+                    crops = self._phi[ckey]
+                    _lib.check(_lib.lib.hd_process_image(C.c_void_p(fr[i:i + n].data_ptr()), n, H, W, C.c_void_p(geom[i:i + n].data_ptr()),
+                                                         C.c_void_p(crops.data_ptr()), size, None, None, 0, st), 'hd_process_image')
+                    plan.run(crops, None, st)
         for i in range(0, N, cB):
             n = min(cB, N - i)
             plan = self._resnet_plan(n, size, 'B')
@@ -268,25 +292,39 @@ class HMMREngine(object):
 
     FETCH_KEYS = tuple(a + b for b in ('', '_delta') for a in ('cams', 'joints', 'kps', 'poses', 'shapes', 'verts', 'omegas'))
 
-    def predict_host(self, images_host, single_frame=False, fetch=None):
+    HOST_RING = 2            # result buffer sets handed out in turn: a returned dict stays valid for HOST_RING - 1 more calls
+
+    def predict_host(self, images_host, single_frame=False, fetch=None, bbox_params=None):
         """The one host->device->host crossing of `sess.run(fetch_dict, feed_dict)` (tester.py:239-258).
 
-        images_host: (B,T,S,S,3) float32 CPU tensor (pinned for real overlap).  Frames go up in `frame_chunk`
-        pieces on a copy stream while the ResNet consumes earlier pieces; results come back into pinned host
-        buffers owned by the engine.  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes); the copies are only
-        complete after `torch.cuda.current_stream().synchronize()`.
-        """
-        if images_host.is_cuda or images_host.dtype != torch.float32 or images_host.dim() != 5:
-            raise _lib.HDError('predict_host: expected a float32 CPU tensor (B,T,S,S,3)')
-        B, T, S = images_host.shape[0], images_host.shape[1], images_host.shape[2]
+        images_host: (B,T,S,S,3) float32 CPU tensor -- the crops `Tester.predict` is fed -- or, with `bbox_params` (B,T,3),
+        (B,T,H,W,3) uint8 video frames that process_image (run_video.py:56-107) crops on the GPU (4x fewer bytes per sample
+        over PCIe, and no host-side resize).  Pinned (or cudaHostRegister-ed) memory gives real overlap: frames go up in
+        H2D_PIECE pieces on a copy stream while the ResNet consumes earlier pieces; results come back into pinned host
+        buffers owned by the engine (a ring of HOST_RING sets).  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes); the
+        copies are only complete after `torch.cuda.current_stream().synchronize()`."""
+        u8 = bbox_params is not None
+        if images_host.is_cuda or images_host.dim() != 5 or images_host.dtype != (torch.uint8 if u8 else torch.float32):
+            raise _lib.HDError('predict_host: expected a CPU tensor (B,T,S,S,3) float32, or (B,T,H,W,3) uint8 with bbox_params')
+        B, T = images_host.shape[0], images_host.shape[1]
         N = B * T
-        flat = images_host.reshape(N, S, S, 3)
-        key = ('img', N, S)
+        flat = images_host.reshape((N,) + tuple(images_host.shape[2:]))
+        key = ('img', N, tuple(flat.shape[1:]), flat.dtype)
         if key not in self._phi:
-            self._phi[key] = torch.empty((N, S, S, 3), dtype=torch.float32, device=self.device)
-            self._phi[('phi', N)] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
+            self._phi[key] = torch.empty(tuple(flat.shape), dtype=flat.dtype, device=self.device)
             self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
+        if ('phi', N) not in self._phi:
+            self._phi[('phi', N)] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
         dev_img, phi = self._phi[key], self._phi[('phi', N)]
+        geom_dev = None
+        if u8:
+            from .preprocess import geometry_table
+            g, _ = geometry_table((flat.shape[1], flat.shape[2]), np.asarray(bbox_params, np.float64).reshape(N, 3), int(self.config.img_size))
+            gkey = ('geom', N)
+            if gkey not in self._phi:
+                self._phi[gkey] = (torch.empty((N, 4), dtype=torch.int32, pin_memory=True), torch.empty((N, 4), dtype=torch.int32, device=self.device))
+            self._phi[gkey][0].copy_(torch.from_numpy(g))
+            geom_dev = self._phi[gkey][1]
         chunk = self.H2D_PIECE
         starts = list(range(0, N, chunk))
         ekey = ('ev', len(starts))
@@ -297,19 +335,26 @@ class HMMREngine(object):
         cs = self._copy_stream
         cs.wait_stream(main)                         # the previous step may still read dev_img
         with torch.cuda.stream(cs):
+            if u8:
+                geom_dev.copy_(self._phi[('geom', N)][0], non_blocking=True)
             for ev, i in zip(events, starts):
                 n = min(chunk, N - i)
                 dev_img[i:i + n].copy_(flat[i:i + n], non_blocking=True)
                 ev.record(cs)
-        self._trunk(dev_img, phi, events)
+        if u8:
+            self._trunk(None, phi, events, frames=(dev_img, geom_dev))
+        else:
+            self._trunk(dev_img, phi, events)
         want = list(fetch or self.FETCH_KEYS)
         host, counted = {}, [0]
+        self._host_slot = (getattr(self, '_host_slot', -1) + 1) % self.HOST_RING
+        slot = self._host_slot
 
         def to_host(tensors, stream):
             for k, v in tensors.items():
                 if k not in want or k in host:
                     continue
-                hk = ('host', k, tuple(v.shape))
+                hk = ('host', slot, k, tuple(v.shape))
                 if hk not in self._phi:
                     self._phi[hk] = torch.empty(tuple(v.shape), dtype=torch.float32, pin_memory=True)
                 with torch.cuda.stream(stream):
@@ -327,7 +372,7 @@ class HMMREngine(object):
         to_host({k: v for k, v in out.items() if not k.startswith('_')}, main)
         main.wait_stream(cs)                  # one synchronisation point for the caller: the current stream
         d2h = counted[0]
-        return host, flat.numel() * 4, d2h
+        return host, flat.numel() * flat.element_size() + (N * 16 if u8 else 0), d2h
 
     def predict_from_features(self, phi, single_frame=False, on_main_ready=None):
         B, T = phi.shape[0], phi.shape[1]

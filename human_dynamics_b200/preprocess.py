@@ -70,5 +70,13 @@ def process_images(frames, bbox_params, img_size=IMG_SIZE, out=None, split_out=N
     elif tuple(out.shape) != (N, img_size, img_size, 3) or out.dtype != torch.float32 or not out.is_contiguous():
         raise _lib.HDError('process_images: out must be a contiguous float32 (N,%d,%d,3) CUDA tensor' % (img_size, img_size))
     check(lib.hd_process_image(C.c_void_p(frames.data_ptr()), N, H, W, C.c_void_p(g_dev.data_ptr()), C.c_void_p(out.data_ptr()),
-                               img_size, current_stream()), 'hd_process_image')
+                               img_size, None, None, 0, current_stream()), 'hd_process_image')
     return out, geoms
+
+
+def geometry_table(im_shape, bbox_params, img_size=IMG_SIZE):
+    """int32 [N,4] = {Hs, Ws, x0, y0} rows for hd_process_image + the per-frame info dicts."""
+    bbox_params = np.asarray(bbox_params, np.float64).reshape(-1, 3)
+    geoms = [crop_geometry(im_shape, b, img_size) for b in bbox_params]
+    g = np.array([[q['new_size'][0], q['new_size'][1], q['origin'][0], q['origin'][1]] for q in geoms], np.int32)
+    return g, geoms

@@ -126,8 +126,11 @@ int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, f
 /* ---- crop pre-processing, the caller of the path: process_image (src/evaluation/run_video.py:56-107) + resize_img
  * (src/util/common.py:7-14), batched.  frames uint8 [N,H,W,3]; geom int32 [N,4] (16-byte aligned) = {Hs, Ws, x0, y0}: size of the
  * cv2.resize'd frame and the top-left corner of the SxS crop in its coordinates (may lie outside: edge replication = the
- * reference's np.pad(mode='edge')); out fp32 [N,S,S,3] = crop of resize(2*(frame/255 - 0.5)) (bilinear, cv2 conventions). */
-int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *stream);
+ * reference's np.pad(mode='edge')); out fp32 [N,S,S,3] = crop of resize(2*(frame/255 - 0.5)) (bilinear, cv2 conventions).
+ * plane_hi / plane_lo (optional, both or neither; then `out` may be NULL): the same crop written directly as the padded RGBX
+ * fp16 planes [N,S+6,WP,4] the tensor-core conv1 reads (hd_pack_conv1_planes layout; border cleared once by the caller). */
+int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *plane_hi,
+                     void *plane_lo, int WP, void *stream);
 
 /* ---- f_movie GroupNorm statistics (tf.contrib.layers.group_norm at src/models.py:155,188) ----
  * x [B,T,C]; per (clip, group) mean / biased variance over T*(C/groups) elements (two-pass);

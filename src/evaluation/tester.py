@@ -52,16 +52,56 @@ class Tester(object):
         self.smpl = self.engine.smpl
         _rt.set_default_engine(self.engine)
         self._pinned = {}
+        self._registered = {}
 
-    def predict(self, images, as_numpy=True):
-        """Runs forward pass of model.  images (BxTxHxWx3) numpy / torch (host or device) -> dict."""
+    MAX_REGISTERED = 2
+
+    def _as_pinned(self, arr):
+        """A CPU tensor over the caller's numpy buffer that the copy engine can read asynchronously.
+
+        The reference's `sess.run(feed_dict=...)` copies the array into TF's own staging memory first; here the caller's
+        buffer itself is page-locked in place (cudaHostRegister, once per buffer -- a video loop that refills the same
+        array pays it once).  Falls back to a staged copy through an engine-owned pinned buffer if registration fails."""
+        t = torch.from_numpy(arr)
+        if t.is_pinned():
+            return t
+        key = (arr.ctypes.data, arr.nbytes)
+        if key not in self._registered:
+            while len(self._registered) >= self.MAX_REGISTERED:
+                old_key, _ = next(iter(self._registered.items()))
+                torch.cuda.cudart().cudaHostUnregister(old_key[0])
+                del self._registered[old_key]
+            rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+            if int(rc) != 0:
+                skey = (tuple(arr.shape), arr.dtype.str)
+                if skey not in self._pinned:
+                    self._pinned[skey] = torch.empty(tuple(arr.shape), dtype=t.dtype, pin_memory=True)
+                self._pinned[skey].copy_(t)
+                return self._pinned[skey]
+            self._registered[key] = arr                      # keeps the buffer alive while it is page-locked
+        return t
+
+    def __del__(self):
+        try:
+            for key in list(getattr(self, '_registered', {})):
+                torch.cuda.cudart().cudaHostUnregister(key[0])
+        except Exception:
+            pass
+
+    def predict(self, images, as_numpy=True, copy=False):
+        """Runs forward pass of model.  images (BxTxHxWx3) numpy / torch (host or device) -> dict (tester.py:229-258).
+
+        Host input = ONE overlapped host->device->host crossing, like sess.run(fetch_dict, feed_dict): the frames stream
+        up in pieces while the ResNet runs, all 14 fetch tensors come back into pinned host memory.  The returned numpy
+        arrays are views of engine-owned result buffers that are recycled every `HMMREngine.HOST_RING` calls; pass
+        copy=True for arrays you own (what sess.run returns) at the price of a 160 MB host memcpy per call."""
         B, T = self.batch_size, self.sequence_length
         exp = (B, T, self.img_size, self.img_size, 3)
         if tuple(images.shape) != exp:
             raise ValueError('images must have the static shape %s baked at construction (tester.py:64-66), got %s'
                              % (exp, tuple(images.shape)))
         if isinstance(images, np.ndarray):
-            images = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+            images = self._as_pinned(np.ascontiguousarray(images, dtype=np.float32))
         if images.is_cuda:
             out = self.engine.predict(images.float())
             out = {k: v for k, v in out.items() if not k.startswith('_')}
@@ -69,16 +109,28 @@ class Tester(object):
                 return out
             torch.cuda.current_stream().synchronize()
             return {k: v.cpu().numpy() for k, v in out.items()}
-        # host input: one overlapped host->device->host crossing, like sess.run(fetch_dict, feed_dict) (tester.py:257)
-        key = tuple(images.shape)
-        if key not in self._pinned:
-            self._pinned[key] = torch.empty(key, dtype=torch.float32, pin_memory=True)
-        self._pinned[key].copy_(images)
-        host, _, _ = self.engine.predict_host(self._pinned[key])
+        host, _, _ = self.engine.predict_host(images if images.dtype == torch.float32 else images.float())
         torch.cuda.current_stream().synchronize()
         if not as_numpy:
             return host
-        return {k: v.numpy().copy() for k, v in host.items()}
+        return {k: (v.numpy().copy() if copy else v.numpy()) for k, v in host.items()}
+
+    def predict_frames(self, frames, bbox_params, as_numpy=True, copy=False):
+        """process_image + predict in one crossing: frames (BxTxHxWx3) uint8 video frames, bbox_params (BxTx3) [cx, cy, scale]
+        (run_video.py:56-107 then tester.py:229).  The crop runs on the GPU from the uint8 frames (1 byte per sample over
+        PCIe instead of 4) and writes the ResNet's first-layer input format directly.  Same result dict as `predict`."""
+        B, T = self.batch_size, self.sequence_length
+        if tuple(frames.shape[:2]) != (B, T) or frames.shape[-1] != 3 or len(frames.shape) != 5:
+            raise ValueError('frames must be (%d,%d,H,W,3) uint8' % (B, T))
+        if isinstance(frames, np.ndarray):
+            if frames.dtype != np.uint8:
+                raise ValueError('frames must be uint8')
+            frames = self._as_pinned(np.ascontiguousarray(frames))
+        host, _, _ = self.engine.predict_host(frames, bbox_params=np.asarray(bbox_params, np.float64).reshape(B, T, 3))
+        torch.cuda.current_stream().synchronize()
+        if not as_numpy:
+            return host
+        return {k: (v.numpy().copy() if copy else v.numpy()) for k, v in host.items()}
 
     def predict_all_images(self, all_images, cache_features=True):
         """Sliding-window prediction over a whole sequence (tester.py:260-312).  all_images: N x H x W x 3.
@@ -124,7 +176,7 @@ class Tester(object):
                                             np.zeros((num_fill, H, W, 3), np.float32)), axis=0)
             for c in range(count):
                 batch = np.stack([images_padded[(c * B + i) * g:(c * B + i) * g + T] for i in range(B)])
-                pred = self.predict(batch)
+                pred = self.predict(batch, copy=True)            # results are kept across calls here
                 for k, v in pred.items():
                     results.setdefault(k, []).append(v)
         new_results = {}

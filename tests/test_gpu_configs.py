@@ -228,3 +228,42 @@ def test_cuda_graph_replay_equals_eager(weights, smpl_model):
     assert _lib.lib.hd_launch_count() == 0          # nothing was launched from the host: the graph did it
     for k in eager_b:
         assert torch.equal(out[k], eager_b[k]), k
+
+
+def test_tester_host_paths_numpy_and_uint8_frames(weights, smpl_model):
+    """Tester.predict on a plain numpy array (page-locked in place) and Tester.predict_frames on uint8 video frames
+    (GPU process_image feeding conv1 directly) against the device path and the cv2 + torch oracle."""
+    pytest.importorskip('cv2')
+    from human_dynamics_b200 import HMMRConfig
+    from human_dynamics_b200.preprocess import process_images
+    from src.evaluation.tester import Tester
+    from oracle import nets_ref, preproc_ref
+    B, T, H, W = 2, 20, 150, 200
+    cfg = HMMRConfig(batch_size=B, sequence_length=T, weights=weights, smpl_model=smpl_model)
+    tester = Tester(cfg)
+    rng = np.random.RandomState(3)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames = np.stack([np.clip((120 + 90 * np.sin(xx / (5.0 + i) + i) * np.cos(yy / 6.0))[..., None] + rng.randint(-30, 30, size=(H, W, 3)), 0, 255)
+                       for i in range(B * T)]).astype(np.uint8).reshape(B, T, H, W, 3)
+    boxes = np.stack([rng.uniform(60, 140, B * T), rng.uniform(40, 110, B * T), rng.uniform(0.8, 1.6, B * T)], axis=1).reshape(B, T, 3)
+    # (1) uint8 frames: one crossing
+    got_u8 = {k: v.copy() for k, v in tester.predict_frames(frames, boxes).items()}
+    # (2) the two-step route: GPU crops -> predict on the device
+    crops, _ = process_images(frames.reshape(B * T, H, W, 3), boxes.reshape(-1, 3))
+    dev = tester.predict(crops.view(B, T, 224, 224, 3), as_numpy=True)
+    for k in dev:
+        assert np.array_equal(got_u8[k], dev[k]), k
+    # (3) a plain (pageable) numpy array of crops through Tester.predict: page-locked in place, same numbers
+    crops_np = crops.cpu().numpy().reshape(B, T, 224, 224, 3).copy()
+    got_np = tester.predict(crops_np)
+    assert len(tester._registered) == 1
+    for k in dev:
+        assert np.array_equal(got_np[k], dev[k]), k
+    again = tester.predict(crops_np)                   # same buffer: no second registration, next ring slot
+    assert len(tester._registered) == 1 and again['verts'] is not got_np['verts']
+    assert np.array_equal(again['verts'], got_np['verts'])
+    # (4) against the reference restatement end to end (cv2 process_image -> oracle graph), clip 0
+    ref_crops = np.stack([preproc_ref.process_image(frames[0, t], boxes[0, t])['image'] for t in range(T)]).astype(np.float32)
+    ref = nets_ref.hmmr_predict(ref_crops[None], weights, smpl_model)
+    for k in ('omegas', 'verts', 'kps', 'verts_delta'):
+        assert rel_err(got_u8[k][:1], ref[k]) < REL, (k, rel_err(got_u8[k][:1], ref[k]))
