@@ -249,10 +249,28 @@ def main():
             if world > 1:
                 last['g'] = gather_outputs({k: out[k] for k in gather_keys}, B * world, dst=0)
 
+        # end to end through the reference-named API: src.evaluation.tester.Tester.predict on a PLAIN numpy array (pageable memory,
+        # page-locked in place on first sight), numpy results back.  The single-frame workload has no Tester wiring in the
+        # reference: it goes through HMMREngine.predict_host with the same copies.
+        from src.evaluation.tester import Tester
+        tester = Tester(cfg, engine=eng)
+        img_np = np.array(img_host.numpy(), copy=True)
+        FR = 256                                          # synthetic uint8 "video frames" for the process_image leg
+        rng = np.random.RandomState(7 + rank)
+        frames_u8 = rng.randint(0, 256, size=(B, Tw, FR, FR, 3), dtype=np.uint8)
+        boxes = np.stack([rng.uniform(100, 156, B * Tw), rng.uniform(100, 156, B * Tw), rng.uniform(0.9, 1.2, B * Tw)], axis=1).reshape(B, Tw, 3)
+
         def step_e2e():
-            host, h2d, d2h = eng.predict_host(img_host, single_frame=single)
-            torch.cuda.current_stream().synchronize()
-            return h2d, d2h
+            if single:
+                host, h2d, d2h = eng.predict_host(img_host, single_frame=True)
+                torch.cuda.current_stream().synchronize()
+                return h2d, d2h
+            res = tester.predict(img_np)
+            return img_np.nbytes, sum(v.nbytes for v in res.values())
+
+        def step_e2e_u8():
+            res = tester.predict_frames(frames_u8, boxes)
+            return frames_u8.nbytes + B * Tw * 16, sum(v.nbytes for v in res.values())
 
     # ------------------------------------------------------------------ device-resident timing (value)
     sampler = ClockSampler(local_rank)
@@ -299,8 +317,28 @@ def main():
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
             sec = float(ts.item())
         e2e = {'value': units_per_step * world / sec, 'unit': unit_name, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': sec * 1e3, 'api': 'HMMREngine.predict_host (= Tester.predict on host arrays): pinned H2D in frame chunks '
-               'overlapped with ResNet, all 14 fetch tensors D2H'}
+               'ms_per_step': sec * 1e3,
+               'api': ('HMMREngine.predict_host(pinned float32 frames), single_frame=True' if single else
+                       'src.evaluation.tester.Tester.predict(np.ndarray float32 (B,T,224,224,3)) -> dict of 14 numpy arrays; the '
+                       "caller's pageable array is page-locked in place once (cudaHostRegister), H2D in 32-frame pieces overlapped with "
+                       'the ResNet, results are views of a 2-deep ring of pinned buffers (copy=False)')}
+        if not single:
+            for _ in range(2):
+                step_e2e_u8()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                h2d8, d2h8 = step_e2e_u8()
+            torch.cuda.synchronize()
+            sec8 = (time.perf_counter() - t0) / args.steps
+            if world > 1:
+                ts = torch.tensor([sec8], device=dev)
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                sec8 = float(ts.item())
+            e2e['uint8_frames'] = {'value': units_per_step * world / sec8, 'unit': unit_name, 'h2d_bytes_per_step': int(h2d8),
+                                   'd2h_bytes_per_step': int(d2h8), 'ms_per_step': sec8 * 1e3,
+                                   'api': 'Tester.predict_frames(uint8 (B,T,%d,%d,3) video frames + bbox [cx,cy,scale]): process_image '
+                                          '(run_video.py:56-107) on the GPU feeding conv1 directly, then the same path' % (FR, FR)}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel (instrumented extra pass)
     roofline = None
