@@ -672,8 +672,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           uint8_t *hrow = buf + C::EPI_F32_BYTES + row * 64;
           uint8_t *lrow = hrow + C::EPI_H_BYTES;
           const int cb = n0 + sl * 32;
+          const bool slab_ok = cb < p.Cout;             // ragged last N tile (Cout % 32 == 0): whole slabs beyond Cout are skipped
 #pragma unroll
           for (int h = 0; h < 4; ++h) {                 // 8 columns: two fp32 chunks, one fp16 chunk
+            if (!slab_ok) break;
             float y[8];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -726,8 +728,8 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           named_bar_sync(1, 128);
           if (epi_leader) {
             const uint32_t sb = smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
-            if (has_o32) tma_store_2d(&em.out, sb, cb, m0);
-            if (has_o16) {
+            if (has_o32 && slab_ok) tma_store_2d(&em.out, sb, cb, m0);
+            if (has_o16 && slab_ok) {
               tma_store_2d(&em.ohi, sb + C::EPI_F32_BYTES, cb, m0);
               tma_store_2d(&em.olo, sb + C::EPI_F32_BYTES + C::EPI_H_BYTES, cb, m0);
             }

@@ -3,7 +3,7 @@
 //
 // Replaces src/tf_smpl/batch_smpl.py:89-162, batch_lbs.py:15-60,133-194, projection.py:16-29 of the
 // reference (one TF op + HBM round trip per line there; three kernels and no materialised W/T here).
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace {
 
@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
                                                         const float *__restrict__ J_shapedirs, float *__restrict__ Rs,
                                                         float *__restrict__ Rs_out, float *__restrict__ Jtr,
                                                         float *__restrict__ A12, int N, int out_mul, int out_off,
-                                                        float *__restrict__ coef, int coef_ld) {
+                                                        float *__restrict__ coef, int coef_ld, __half *__restrict__ coef_hi,
+                                                        __half *__restrict__ coef_lo) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -131,6 +132,23 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
       } else {
 #pragma unroll
         for (int i = 0; i < 9; ++i) cr[10 + (lane - 1) * 9 + i] = R[i] - ((i == 0 || i == 4 || i == 8) ? 1.0f : 0.0f);
+      }
+    }
+    if (coef_hi) {     // the same operand row, pre-split into the fp16 head / 2^11-scaled remainder pair the tensor-core kernel loads
+      __half *ch = coef_hi + (size_t)n * coef_ld, *cl = coef_lo + (size_t)n * coef_ld;
+      auto put = [&](int k, float x) {
+        uint32_t h, l;
+        hd::split_f16x2(x, 0.f, h, l);
+        ch[k] = __ushort_as_half((unsigned short)(h & 0xffffu));
+        cl[k] = __ushort_as_half((unsigned short)(l & 0xffffu));
+      };
+      if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < 10; ++b) put(b, __ldg(beta + (size_t)n * beta_ld + b));
+        for (int k = 217; k < coef_ld; ++k) put(k, 0.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) put(10 + (lane - 1) * 9 + i, R[i] - ((i == 0 || i == 4 || i == 8) ? 1.0f : 0.0f));
       }
     }
     float4 *a = reinterpret_cast<float4 *>(A12 + ((size_t)n * 24 + lane) * 12);
@@ -424,7 +442,7 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   float *A12 = reinterpret_cast<float *>(ws);
   float *Rs_w = A12 + (size_t)N * 288;
-  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off, nullptr, 0);
+  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off, nullptr, 0, nullptr, nullptr);
   int rc = hd::check_launch("smpl_pose_kernel");
   if (rc) return rc;
   const bool big = N >= 32 * 148;
@@ -440,17 +458,18 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
 
 // ---- staged SMPL (tensor-core blend): pose -> [hd_conv_gemm: v_posed = coef . dirs + v_template] -> lbs -> joints ----
 int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
-                 float *Jtr, float *A12, float *coef, int coef_ld, int out_mul, int out_off, void *ws, size_t ws_bytes,
-                 void *stream) {
+                 float *Jtr, float *A12, float *coef, int coef_ld, void *coef_hi, void *coef_lo, int out_mul, int out_off, void *ws,
+                 size_t ws_bytes, void *stream) {
   HD_REQUIRE(c && beta && theta && A12 && ws && N > 0 && beta_ld >= 10 && theta_ld >= 72 && out_mul >= 1 && out_off >= 0 &&
-                 out_off < out_mul && (!coef || coef_ld >= 217),
+                 out_off < out_mul && ((!coef && !coef_hi) || coef_ld >= 217) && ((coef_hi == nullptr) == (coef_lo == nullptr)),
              "hd_smpl_pose: bad arguments");
   if (ws_bytes < (size_t)N * 216 * sizeof(float)) return HD_ERR_WORKSPACE;
   Tree tree;
   if (!build_tree(c->parents, tree)) { hd::set_last_error_text("hd_smpl_pose: parents must satisfy parent[i] < i"); return HD_ERR_INVALID; }
   smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template,
                                                                           c->J_shapedirs, reinterpret_cast<float *>(ws), Rs, Jtr,
-                                                                          A12, N, out_mul, out_off, coef, coef_ld);
+                                                                          A12, N, out_mul, out_off, coef, coef_ld,
+                                                                          reinterpret_cast<__half *>(coef_hi), reinterpret_cast<__half *>(coef_lo));
   return hd::check_launch("smpl_pose_kernel");
 }
 

@@ -202,17 +202,21 @@ class SMPLConstants(object):
         """pose -> tensor-core blend GEMM -> skinning -> keypoints (hd_smpl_pose / hd_conv_gemm / hd_smpl_lbs / hd_smpl_joints)."""
         dev = beta.device
         if N not in self._tc_bufs:
+            while len(self._tc_bufs) >= 3:                     # bounded cache: an entry holds N * 83 KB of v_posed
+                self._tc_bufs.pop(next(iter(self._tc_bufs)))
             f32 = dict(dtype=torch.float32, device=dev)
-            coef = torch.empty((N, 256), **f32)
+            coef = (torch.empty((N, 256), dtype=torch.float16, device=dev), torch.empty((N, 256), dtype=torch.float16, device=dev))
             vpos = torch.empty((N, self.vp_ld), **f32)
             a12 = torch.empty((N, 288), **f32)
             rsw = torch.empty((N, 216), **f32)
-            op = self.blend.bind(coef, N, 1, 1, vpos, impl='tc3h')
+            # operand rows arrive pre-split from the pose kernel: cp.async producer + TMA-store epilogue (K = 256)
+            op = self.blend.bind(None, N, 1, 1, vpos, inp_split=coef, impl='tc3h')
             self._tc_bufs[N] = (coef, vpos, a12, rsw, op)
         coef, vpos, a12, rsw, op = self._tc_bufs[N]
         st = current_stream()
         check(lib.hd_smpl_pose(C.byref(self.c), fptr(beta), beta.stride(0), fptr(theta), theta.stride(0), N, fptr(Rs), fptr(Jtr),
-                               fptr(a12), fptr(coef), 256, mul, off, dptr(rsw), rsw.numel() * 4, st), 'hd_smpl_pose')
+                               fptr(a12), None, 256, C.c_void_p(coef[0].data_ptr()), C.c_void_p(coef[1].data_ptr()), mul, off,
+                               dptr(rsw), rsw.numel() * 4, st), 'hd_smpl_pose')
         op.run(st)
         check(lib.hd_smpl_lbs(C.byref(self.c), fptr(vpos), self.vp_ld, fptr(a12), fptr(verts), N, mul, off, st), 'hd_smpl_lbs')
         if (joints is not None or kps is not None) and self.num_kps > 0:

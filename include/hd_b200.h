@@ -173,8 +173,9 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
  * hd_conv_gemm -> hd_smpl_lbs (skinning of the blended v_posed [N, vp_ld]) -> hd_smpl_joints (keypoints + projection).
  * ws of hd_smpl_pose: N*216 floats. */
 int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
-                 float *Jtr, float *A12, float *coef, int coef_ld, int out_mul, int out_off, void *ws, size_t ws_bytes,
-                 void *stream);
+                 float *Jtr, float *A12, float *coef /* fp32 rows, nullable */, int coef_ld,
+                 void *coef_hi, void *coef_lo /* the same rows as an fp16 head / 2^11-scaled remainder pair, nullable */,
+                 int out_mul, int out_off, void *ws, size_t ws_bytes, void *stream);
 int hd_smpl_lbs(const hd_smpl_consts *c, const float *v_posed, long long vp_ld, const float *A12, float *verts, int N, int out_mul,
                 int out_off, void *stream);
 int hd_smpl_joints(const hd_smpl_consts *c, const float *verts, const float *cam, int cam_ld, float *joints, float *kps, int N,

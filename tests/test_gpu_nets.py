@@ -126,6 +126,8 @@ def test_conv_gemm_tcgen05_3xf16(case):
     (9, 14, 128, 512, 1, 1, True, False),    # residual + split output only (no fp32 store)
     (9, 14, 256, 1024, 1, 1, False, True),   # no residual, both outputs
     (300, 14, 64, 256, 1, 1, True, True),    # 460 M-tiles x 2: every CTA walks ~6 tiles (ring wrap-around, barrier phases)
+    (5, 14, 128, 96, 1, 1, True, True),      # Cout = 96: one 128-wide N tile whose last 32-column slab lies outside the tensor
+    (6, 14, 256, 160, 1, 1, False, True),    # Cout = 160: second N tile has 1 valid slab of 4
 ])
 @pytest.mark.parametrize('tma', [True, False])
 def test_conv_gemm_presplit_activations(shape, tma, monkeypatch):
