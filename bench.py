@@ -199,7 +199,7 @@ def main():
     import torch.distributed as dist
     from human_dynamics_b200 import synthetic, HMMRConfig, _lib
     from human_dynamics_b200.engine import HMMREngine
-    from human_dynamics_b200.dist import gather_outputs
+    from human_dynamics_b200.dist import OutputGatherer
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -240,14 +240,24 @@ def main():
         gather_keys = ('omegas', 'verts', 'kps')          # per-clip outputs named by BASELINE config 4 / SURVEY 8e
         last = {}
 
+        gatherer = OutputGatherer(B * world, dst=0) if world > 1 else None
+
         def step():
-            if args.graph:
+            if world > 1:
+                # eager launches so that the dt=0 outputs start travelling to rank 0 (side stream, point-to-point over NVLink)
+                # while the delta heads still compute; the delta-independent keys need nothing else
+                def main_ready(o):
+                    gatherer.start({k: o[k] for k in gather_keys if k in o})
+                out = eng.predict(img_dev, single_frame=single, on_main_ready=main_ready)
+                rest = {k: out[k] for k in gather_keys if k.endswith('_delta')}
+                if rest:
+                    gatherer.start(rest)
+                last['g'] = gatherer.wait()
+            elif args.graph:
                 out, last['nodes'] = eng.predict_graphed(img_dev, single_frame=single)
             else:
                 out = eng.predict(img_dev, single_frame=single)
             last['out'] = out
-            if world > 1:
-                last['g'] = gather_outputs({k: out[k] for k in gather_keys}, B * world, dst=0)
 
         # end to end through the reference-named API: src.evaluation.tester.Tester.predict on a PLAIN numpy array (pageable memory,
         # page-locked in place on first sight), numpy results back.  The single-frame workload has no Tester wiring in the
@@ -261,6 +271,13 @@ def main():
         boxes = np.stack([rng.uniform(100, 156, B * Tw), rng.uniform(100, 156, B * Tw), rng.uniform(0.9, 1.2, B * Tw)], axis=1).reshape(B, Tw, 3)
 
         def step_e2e():
+            if world > 1:      # N GPUs: the end-to-end step includes the gather of the per-clip outputs onto rank 0 (device tensors there)
+                def main_ready(o):
+                    gatherer.start({k: o[k] for k in gather_keys if k in o})
+                host, h2d, d2h = eng.predict_host(img_host, single_frame=single, on_main_ready=main_ready)
+                last['g'] = gatherer.wait()
+                torch.cuda.current_stream().synchronize()
+                return h2d, d2h
             if single:
                 host, h2d, d2h = eng.predict_host(img_host, single_frame=True)
                 torch.cuda.current_stream().synchronize()

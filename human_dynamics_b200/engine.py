@@ -255,7 +255,7 @@ class HMMREngine(object):
         return self._outs[key]
 
     # ---------------------------------------------------------------- full window
-    def predict(self, images, single_frame=False):
+    def predict(self, images, single_frame=False, on_main_ready=None):
         """Tester.predict on device.  images (B,T,S,S,3) float32 CUDA -> dict of CUDA tensors with the 14
         fetch keys of tester.py:217-255 (+ '_phi', '_movie_strips' for inspection).  Outputs are plan-owned
         buffers that the next predict() of the same shape overwrites."""
@@ -267,7 +267,7 @@ class HMMREngine(object):
         if key not in self._phi:
             self._phi[key] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
         phi = self.encode_images(images.reshape((N,) + tuple(images.shape[2:])), out=self._phi[key])
-        return self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame)
+        return self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame, on_main_ready=on_main_ready)
 
     def predict_graphed(self, images, single_frame=False):
         """`predict` replayed from a CUDA graph: the ~190 kernel launches of a window are captured once per input buffer /
@@ -294,7 +294,7 @@ class HMMREngine(object):
 
     HOST_RING = 2            # result buffer sets handed out in turn: a returned dict stays valid for HOST_RING - 1 more calls
 
-    def predict_host(self, images_host, single_frame=False, fetch=None, bbox_params=None):
+    def predict_host(self, images_host, single_frame=False, fetch=None, bbox_params=None, on_main_ready=None):
         """The one host->device->host crossing of `sess.run(fetch_dict, feed_dict)` (tester.py:239-258).
 
         images_host: (B,T,S,S,3) float32 CPU tensor -- the crops `Tester.predict` is fed -- or, with `bbox_params` (B,T,3),
@@ -367,6 +367,8 @@ class HMMREngine(object):
             ev.record(main)
             cs.wait_event(ev)
             to_host(main_out, cs)
+            if on_main_ready is not None:    # (multi-GPU: the same moment starts the gather towards rank 0)
+                on_main_ready(main_out)
 
         out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame, on_main_ready=main_ready)
         to_host({k: v for k, v in out.items() if not k.startswith('_')}, main)

@@ -19,7 +19,7 @@ if ROOT not in sys.path:
 def main():
     from human_dynamics_b200 import synthetic, HMMRConfig
     from human_dynamics_b200.engine import HMMREngine
-    from human_dynamics_b200.dist import shard_range, gather_outputs
+    from human_dynamics_b200.dist import shard_range, gather_outputs, OutputGatherer, TRANSFER_KEYS_ALL
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
@@ -35,6 +35,12 @@ def main():
     keys = [k for k in out if not k.startswith('_')]
     local_out = {k: out[k].contiguous() for k in keys}
     gathered = gather_outputs(local_out, clips, dst=0)
+    # the overlapped point-to-point gatherer bench.py uses: dt=0 keys start while the delta heads run; 10 keys travel, 4 are derived
+    g = OutputGatherer(clips, dst=0)
+    out2 = eng.predict(torch.from_numpy(img[lo:hi]).cuda(),
+                       on_main_ready=lambda o: g.start({k: o[k] for k in TRANSFER_KEYS_ALL if k in o}))
+    g.start({k: out2[k] for k in TRANSFER_KEYS_ALL if k.endswith('_delta')})
+    gathered2 = g.wait()
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
@@ -44,8 +50,9 @@ def main():
         torch.cuda.synchronize()
         for k in keys:
             same = torch.equal(gathered[k], full[k].contiguous())
-            print('%-14s %s %s' % (k, tuple(gathered[k].shape), 'bit-identical' if same else 'DIFFERS'))
-            ok = ok and same
+            same2 = torch.equal(gathered2[k].contiguous(), full[k].contiguous())
+            print('%-14s %s %s / p2p %s' % (k, tuple(gathered[k].shape), 'bit-identical' if same else 'DIFFERS', 'bit-identical' if same2 else 'DIFFERS'))
+            ok = ok and same and same2
     else:
         assert gathered is None
     flag = torch.tensor([1 if ok else 0], device='cuda')

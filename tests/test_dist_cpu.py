@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from human_dynamics_b200.dist import gather_outputs, shard_counts, shard_range
+from human_dynamics_b200.dist import OutputGatherer, gather_outputs, shard_counts, shard_range
 
 
 def test_shard_range_partitions_clips():
@@ -41,6 +41,18 @@ def _worker(rank, world, port, clips, q):
         ok = all(torch.equal(got[k], full[k]) for k in full)       # bit-identical, clip order preserved
     else:
         ok = got is None
+    # point-to-point gatherer: two start() calls (dt=0 outputs first, deltas later), one wait; cams / shapes derived on dst
+    full['omegas_delta'] = torch.arange(clips * 20 * 2 * 85, dtype=torch.float32).reshape(clips, 20, 2, 85) + 0.25
+    g = OutputGatherer(clips, dst=0)
+    g.start({k: full[k][a:b].clone() for k in ('omegas', 'kps')})
+    g.start({'omegas_delta': full['omegas_delta'][a:b].clone()})
+    got2 = g.wait()
+    if rank == 0:
+        ok = ok and all(torch.equal(got2[k], full[k]) for k in ('omegas', 'kps', 'omegas_delta'))
+        ok = ok and torch.equal(got2['cams'], full['omegas'][..., 0:3]) and torch.equal(got2['shapes_delta'], full['omegas_delta'][..., 75:85])
+        ok = ok and torch.equal(got2['cams_delta'][:, :, 1], full['omegas'][..., 0:3])
+    else:
+        ok = ok and got2 is None
     q.put((rank, ok))
     dist.destroy_process_group()
 
