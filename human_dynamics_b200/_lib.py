@@ -72,7 +72,8 @@ SIGNATURES = {
     'hd_ief_delta_init': (_i, [_vp, _vp, _i, _i, _vp]),
     'hd_smpl_workspace_bytes': (_sz, [_i]),
     'hd_smpl_forward': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
-    'hd_smpl_pose': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    'hd_smpl_pose': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    'hd_smpl_lbs_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _vp]),
     'hd_smpl_lbs': (_i, [C.POINTER(SmplConsts), _vp, _ll, _vp, _vp, _i, _i, _i, _vp]),
     'hd_smpl_joints': (_i, [C.POINTER(SmplConsts), _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     'hd_rodrigues': (_i, [_vp, _vp, _i, _vp]),

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
                                                         float *__restrict__ Rs_out, float *__restrict__ Jtr,
                                                         float *__restrict__ A12, int N, int out_mul, int out_off,
                                                         float *__restrict__ coef, int coef_ld, __half *__restrict__ coef_hi,
-                                                        __half *__restrict__ coef_lo) {
+                                                        __half *__restrict__ coef_lo, __half *__restrict__ a12t_hi,
+                                                        __half *__restrict__ a12t_lo) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -152,10 +153,27 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(Tree tree, const float *
       }
     }
     float4 *a = reinterpret_cast<float4 *>(A12 + ((size_t)n * 24 + lane) * 12);
+    float av[12];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {                      // A = results - pad(results . [J;0]), batch_lbs.py:188-192
       const float ib = Rw[r * 3 + 0] * J[0] + Rw[r * 3 + 1] * J[1] + Rw[r * 3 + 2] * J[2];
       a[r] = make_float4(Rw[r * 3 + 0], Rw[r * 3 + 1], Rw[r * 3 + 2], tw[r] - ib);
+      av[r * 4 + 0] = Rw[r * 3 + 0]; av[r * 4 + 1] = Rw[r * 3 + 1]; av[r * 4 + 2] = Rw[r * 3 + 2]; av[r * 4 + 3] = tw[r] - ib;
+    }
+    if (a12t_hi) {     // B operand of the tensor-core skinning GEMM (smpl_lbs_tc.cu): [n][entry i][joint k, 32 wide] as an UNSCALED fp16
+                       // head / remainder pair (entries are O(1): the remainder stays far above the fp16 subnormal floor in absolute terms)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const __half h = __float2half_rn(av[i]);
+        a12t_hi[((size_t)n * 12 + i) * 32 + lane] = h;
+        a12t_lo[((size_t)n * 12 + i) * 32 + lane] = __float2half_rn(av[i] - __half2float(h));
+      }
+    }
+  } else if (a12t_hi) {                                // joints 24..31: the zero padding of K
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      a12t_hi[((size_t)n * 12 + i) * 32 + lane] = __float2half_rn(0.f);
+      a12t_lo[((size_t)n * 12 + i) * 32 + lane] = __float2half_rn(0.f);
     }
   }
 }
@@ -442,7 +460,7 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   float *A12 = reinterpret_cast<float *>(ws);
   float *Rs_w = A12 + (size_t)N * 288;
-  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off, nullptr, 0, nullptr, nullptr);
+  smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, st>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template, c->J_shapedirs, Rs_w, Rs, Jtr, A12, N, out_mul, out_off, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
   int rc = hd::check_launch("smpl_pose_kernel");
   if (rc) return rc;
   const bool big = N >= 32 * 148;
@@ -458,10 +476,11 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
 
 // ---- staged SMPL (tensor-core blend): pose -> [hd_conv_gemm: v_posed = coef . dirs + v_template] -> lbs -> joints ----
 int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
-                 float *Jtr, float *A12, float *coef, int coef_ld, void *coef_hi, void *coef_lo, int out_mul, int out_off, void *ws,
-                 size_t ws_bytes, void *stream) {
+                 float *Jtr, float *A12, float *coef, int coef_ld, void *coef_hi, void *coef_lo, void *a12t_hi, void *a12t_lo, int out_mul,
+                 int out_off, void *ws, size_t ws_bytes, void *stream) {
   HD_REQUIRE(c && beta && theta && A12 && ws && N > 0 && beta_ld >= 10 && theta_ld >= 72 && out_mul >= 1 && out_off >= 0 &&
-                 out_off < out_mul && ((!coef && !coef_hi) || coef_ld >= 217) && ((coef_hi == nullptr) == (coef_lo == nullptr)),
+                 out_off < out_mul && ((!coef && !coef_hi) || coef_ld >= 217) && ((coef_hi == nullptr) == (coef_lo == nullptr)) &&
+                 ((a12t_hi == nullptr) == (a12t_lo == nullptr)),
              "hd_smpl_pose: bad arguments");
   if (ws_bytes < (size_t)N * 216 * sizeof(float)) return HD_ERR_WORKSPACE;
   Tree tree;
@@ -469,7 +488,8 @@ int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const 
   smpl_pose_kernel<<<hd::ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(tree, beta, beta_ld, theta, theta_ld, c->J_template,
                                                                           c->J_shapedirs, reinterpret_cast<float *>(ws), Rs, Jtr,
                                                                           A12, N, out_mul, out_off, coef, coef_ld,
-                                                                          reinterpret_cast<__half *>(coef_hi), reinterpret_cast<__half *>(coef_lo));
+                                                                          reinterpret_cast<__half *>(coef_hi), reinterpret_cast<__half *>(coef_lo),
+                                                                          reinterpret_cast<__half *>(a12t_hi), reinterpret_cast<__half *>(a12t_lo));
   return hd::check_launch("smpl_pose_kernel");
 }
 

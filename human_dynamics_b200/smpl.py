@@ -6,6 +6,7 @@ reference-named class lives in src/tf_smpl/batch_smpl.py and delegates here.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 
 import numpy as np
@@ -153,6 +154,13 @@ class SMPLConstants(object):
             bias = np.zeros(self.vp_ld, np.float32)
             bias[:V * 3] = v_template.reshape(-1)
             self.blend = PackedConv(wb, dev, post_shift=bias, tc='tc3h')
+            # dense skinning weights as the A operand of the tensor-core skinning GEMM: [roundup128(V), 32] fp16 head + unscaled remainder
+            wd = np.zeros(((V + 127) // 128 * 128, 32), np.float32)
+            wd[:V, :24] = weights
+            w_hi = wd.astype(np.float16)
+            self.w_hi = torch.from_numpy(w_hi).to(dev)
+            self.w_lo = torch.from_numpy((wd - w_hi.astype(np.float32)).astype(np.float16)).to(dev)
+        self.lbs_tc = bool(tc) and os.environ.get('HD_LBS_TC', '1') != '0' and (V * 3 * 4) % 8 == 0
 
     def workspace(self, N):
         need = int(lib.hd_smpl_workspace_bytes(N))
@@ -209,16 +217,24 @@ class SMPLConstants(object):
             vpos = torch.empty((N, self.vp_ld), **f32)
             a12 = torch.empty((N, 288), **f32)
             rsw = torch.empty((N, 216), **f32)
+            a12t = (torch.empty((N, 12, 32), dtype=torch.float16, device=dev), torch.empty((N, 12, 32), dtype=torch.float16, device=dev)) \
+                if self.lbs_tc else None
             # operand rows arrive pre-split from the pose kernel: cp.async producer + TMA-store epilogue (K = 256)
             op = self.blend.bind(None, N, 1, 1, vpos, inp_split=coef, impl='tc3h')
-            self._tc_bufs[N] = (coef, vpos, a12, rsw, op)
-        coef, vpos, a12, rsw, op = self._tc_bufs[N]
+            self._tc_bufs[N] = (coef, vpos, a12, rsw, op, a12t)
+        coef, vpos, a12, rsw, op, a12t = self._tc_bufs[N]
         st = current_stream()
         check(lib.hd_smpl_pose(C.byref(self.c), fptr(beta), beta.stride(0), fptr(theta), theta.stride(0), N, fptr(Rs), fptr(Jtr),
-                               fptr(a12), None, 256, C.c_void_p(coef[0].data_ptr()), C.c_void_p(coef[1].data_ptr()), mul, off,
+                               fptr(a12), None, 256, C.c_void_p(coef[0].data_ptr()), C.c_void_p(coef[1].data_ptr()),
+                               C.c_void_p(a12t[0].data_ptr()) if a12t else None, C.c_void_p(a12t[1].data_ptr()) if a12t else None, mul, off,
                                dptr(rsw), rsw.numel() * 4, st), 'hd_smpl_pose')
         op.run(st)
-        check(lib.hd_smpl_lbs(C.byref(self.c), fptr(vpos), self.vp_ld, fptr(a12), fptr(verts), N, mul, off, st), 'hd_smpl_lbs')
+        if a12t is not None:       # T = W . A on the tensor cores, applied from TMEM (smpl_lbs_tc.cu)
+            check(lib.hd_smpl_lbs_tc(C.c_void_p(self.w_hi.data_ptr()), C.c_void_p(self.w_lo.data_ptr()), C.c_void_p(a12t[0].data_ptr()),
+                                     C.c_void_p(a12t[1].data_ptr()), fptr(vpos), self.vp_ld, fptr(verts), N, self.num_verts, mul, off, st),
+                  'hd_smpl_lbs_tc')
+        else:
+            check(lib.hd_smpl_lbs(C.byref(self.c), fptr(vpos), self.vp_ld, fptr(a12), fptr(verts), N, mul, off, st), 'hd_smpl_lbs')
         if (joints is not None or kps is not None) and self.num_kps > 0:
             check(lib.hd_smpl_joints(C.byref(self.c), fptr(verts), fptr(cam) if cam is not None else None,
                                      cam.stride(0) if cam is not None else 0, fptr(joints), fptr(kps) if kps is not None else None,

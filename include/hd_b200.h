@@ -175,7 +175,13 @@ int hd_smpl_forward(const hd_smpl_consts *c, const float *beta, int beta_ld, con
 int hd_smpl_pose(const hd_smpl_consts *c, const float *beta, int beta_ld, const float *theta, int theta_ld, int N, float *Rs,
                  float *Jtr, float *A12, float *coef /* fp32 rows, nullable */, int coef_ld,
                  void *coef_hi, void *coef_lo /* the same rows as an fp16 head / 2^11-scaled remainder pair, nullable */,
+                 void *a12t_hi, void *a12t_lo /* [N,12,32] fp16 head / unscaled remainder of A transposed: operand of hd_smpl_lbs_tc, nullable */,
                  int out_mul, int out_off, void *ws, size_t ws_bytes, void *stream);
+/* Skinning with the 6890x24 blend-weight x transform contraction on the tensor cores (batch_smpl.py:141-151):
+ * w_hi / w_lo = dense skinning weights [roundup128(V), 32] (24 joints + zero padding) as an fp16 head / unscaled remainder pair;
+ * a12t_hi / a12t_lo from hd_smpl_pose; v_posed [N, vp_ld] (vp_ld % 4 == 0, >= roundup4(3V)) -> verts slot n*out_mul + out_off. */
+int hd_smpl_lbs_tc(const void *w_hi, const void *w_lo, const void *a12t_hi, const void *a12t_lo, const float *v_posed, long long vp_ld,
+                   float *verts, int N, int V, int out_mul, int out_off, void *stream);
 int hd_smpl_lbs(const hd_smpl_consts *c, const float *v_posed, long long vp_ld, const float *A12, float *verts, int N, int out_mul,
                 int out_off, void *stream);
 int hd_smpl_joints(const hd_smpl_consts *c, const float *verts, const float *cam, int cam_ld, float *joints, float *kps, int N,
