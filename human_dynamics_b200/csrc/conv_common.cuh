@@ -45,7 +45,7 @@ inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
     return HD_ERR_INVALID;
   }
   if (d->n_img <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0 ||
-      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || d->in_ld < d->Cin || (d->out && d->out_ld < d->Cout) || (d->out_hi && d->out2_ld < d->Cout)) {
+      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || (d->in_ld < d->Cin && !(d->flags & HD_CONV_INPUT_PLANES)) || (d->out && d->out_ld < d->Cout) || (d->out_hi && d->out2_ld < d->Cout)) {
     set_last_error_text("hd_conv_gemm: bad shape");
     return HD_ERR_INVALID;
   }
