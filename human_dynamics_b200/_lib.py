@@ -77,6 +77,7 @@ SIGNATURES = {
     'hd_smpl_lbs': (_i, [C.POINTER(SmplConsts), _vp, _ll, _vp, _vp, _i, _i, _i, _vp]),
     'hd_smpl_joints': (_i, [C.POINTER(SmplConsts), _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     'hd_rodrigues': (_i, [_vp, _vp, _i, _vp]),
+    'hd_rot2aa': (_i, [_vp, _vp, _i, _vp]),
     'hd_global_rigid': (_i, [_vp, _vp, C.POINTER(C.c_int), _vp, _vp, _i, _i, _vp]),
     'hd_orth_proj': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
 }

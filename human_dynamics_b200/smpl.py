@@ -258,6 +258,18 @@ def batch_rodrigues(theta):
     return R
 
 
+def batch_rot2aa(Rs):
+    """Rs (B,3,3) float32 CUDA -> axis-angle (B,3).  src/tf_smpl/batch_lbs.py:63-105."""
+    if not Rs.is_cuda:
+        raise _lib.HDError('batch_rot2aa: CUDA tensor required (no CPU fallback exists)')
+    Rs = Rs.contiguous().float()
+    if Rs.dim() != 3 or tuple(Rs.shape[1:]) != (3, 3):
+        raise _lib.HDError('batch_rot2aa: Rs must be (B,3,3)')
+    aa = torch.empty((Rs.shape[0], 3), dtype=torch.float32, device=Rs.device)
+    check(lib.hd_rot2aa(fptr(Rs), fptr(aa), Rs.shape[0], current_stream()), 'hd_rot2aa')
+    return aa
+
+
 def batch_global_rigid_transformation(Rs, Js, parent, rotate_base=False):
     """Rs (N,24,3,3), Js (N,24,3), parent int[24] -> (new_J (N,24,3), A (N,24,4,4)).  batch_lbs.py:133-194."""
     if not (Rs.is_cuda and Js.is_cuda):

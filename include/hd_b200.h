@@ -188,6 +188,8 @@ int hd_smpl_joints(const hd_smpl_consts *c, const float *verts, const float *cam
                    int out_mul, int out_off, void *stream);
 /* batch_rodrigues: theta [M,3] -> R [M,3,3]. */
 int hd_rodrigues(const float *theta, float *R, int M, void *stream);
+/* batch_rot2aa (src/tf_smpl/batch_lbs.py:63-105): R [M,3,3] -> axis-angle [M,3]. */
+int hd_rot2aa(const float *Rs, float *aa, int M, void *stream);
 /* batch_global_rigid_transformation: Rs [N,24,3,3], Js [N,24,3], parents host int[24] -> new_J [N,24,3], A [N,24,4,4]. */
 int hd_global_rigid(const float *Rs, const float *Js, const int *parents_host, float *new_J, float *A44, int N,
                     int rotate_base, void *stream);

@@ -47,6 +47,24 @@ def batch_rodrigues(theta, dtype=np.float32):
     return R.astype(dtype)
 
 
+def batch_rot2aa(Rs, dtype=np.float32):
+    """src/tf_smpl/batch_lbs.py:63-105."""
+    Rs = np.asarray(Rs, dtype)
+    cos = 0.5 * (np.trace(Rs, axis1=1, axis2=2) - 1)                                 # :91
+    cos = np.clip(cos, -1, 1)                                                        # :92
+    theta = np.arccos(cos)                                                           # :94
+    m21 = Rs[:, 2, 1] - Rs[:, 1, 2]
+    m02 = Rs[:, 0, 2] - Rs[:, 2, 0]
+    m10 = Rs[:, 1, 0] - Rs[:, 0, 1]
+    denom = np.sqrt(m21 * m21 + m02 * m02 + m10 * m10)
+    small = np.abs(theta) < 0.00001
+    with np.errstate(divide='ignore', invalid='ignore'):
+        axis0 = np.where(small, m21, m21 / denom)                                    # :101-103
+        axis1 = np.where(small, m02, m02 / denom)
+        axis2 = np.where(small, m10, m10 / denom)
+    return (theta[:, None] * np.stack([axis0, axis1, axis2], 1)).astype(dtype)       # :105
+
+
 def batch_global_rigid_transformation(Rs, Js, parent, rotate_base=False, dtype=np.float32):
     """src/tf_smpl/batch_lbs.py:133-194.  Rs [N,24,3,3], Js [N,24,3] -> new_J [N,24,3], A [N,24,4,4]."""
     Rs = np.asarray(Rs, dtype)

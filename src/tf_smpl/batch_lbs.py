@@ -19,3 +19,9 @@ def batch_rodrigues(theta, name=None):
 def batch_global_rigid_transformation(Rs, Js, parent, rotate_base=False):
     """Rs N x 24 x 3 x 3, Js N x 24 x 3, parent 24 -> (new_J N x 24 x 3, A N x 24 x 4 x 4)   (batch_lbs.py:133-194)."""
     return _global_rigid(Rs, Js, parent, rotate_base)
+
+
+def batch_rot2aa(Rs):
+    """Rs is B x 3 x 3 -> B x 3 axis-angle   (batch_lbs.py:63-105)."""
+    from human_dynamics_b200.smpl import batch_rot2aa as _rot2aa
+    return _rot2aa(Rs)

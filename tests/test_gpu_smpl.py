@@ -151,3 +151,19 @@ def test_smpl_large_batch_properties(smpl_model):
     idx = np.arange(0, n, 1024)
     ref = _oracle(smpl_model, beta[idx], theta[idx])
     assert rel_err(v1[idx].cpu().numpy(), ref['verts']) < REL
+
+
+def test_batch_rot2aa_matches_oracle():
+    """src.tf_smpl.batch_lbs.batch_rot2aa (batch_lbs.py:63-105) on the GPU vs the numpy restatement, incl. identity rows."""
+    from src.tf_smpl.batch_lbs import batch_rot2aa, batch_rodrigues
+    from oracle import smpl_ref
+    rng = np.random.RandomState(2)
+    th = rng.normal(0, 0.8, size=(500, 3)).astype(np.float32)
+    th[::50] = 0.0
+    R = batch_rodrigues(torch.from_numpy(th).cuda())
+    aa = batch_rot2aa(R).cpu().numpy()
+    ref = smpl_ref.batch_rot2aa(R.cpu().numpy().astype(np.float64), np.float64)
+    assert np.abs(aa - ref).max() < 5e-4          # acos near 1 amplifies fp32 rounding of the trace
+    big = np.linalg.norm(th, axis=1) > 0.3
+    assert np.abs(aa[big] - th[big]).max() < 2e-5
+    assert np.all(aa[::50] == 0.0)

@@ -122,3 +122,15 @@ def test_face_table_is_bit_exact_fixture():
     f = np.load(p)
     assert f.shape == (13776, 3) and f.dtype == np.uint32 and f.min() == 0 and f.max() == 6889
     assert hashlib.sha256(open(p, 'rb').read()).hexdigest().startswith('51fc11eb')
+
+
+def test_rot2aa_inverts_rodrigues():
+    """batch_rot2aa (batch_lbs.py:63-105) recovers the axis-angle vector for angles in (0, pi); identity -> 0."""
+    from oracle import smpl_ref
+    rng = np.random.RandomState(0)
+    axis = rng.normal(size=(64, 3)); axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    ang = rng.uniform(0.05, 3.0, size=(64, 1))
+    th = axis * ang
+    R = smpl_ref.batch_rodrigues(th, np.float64)
+    assert np.allclose(smpl_ref.batch_rot2aa(R, np.float64), th, atol=1e-6)
+    assert np.allclose(smpl_ref.batch_rot2aa(np.eye(3)[None], np.float64), 0.0)
