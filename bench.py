@@ -472,6 +472,8 @@ def measure_roofline(args, peaks, env):
         torch.cuda.synchronize()
         for a, b, op in evs:
             d = op.d
+            if d is None:                 # not a conv (strided-shortcut subsample)
+                continue
             fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
             t = a.elapsed_time(b) * 1e-3
             conv_time += t * reps

@@ -66,6 +66,7 @@ SIGNATURES = {
     'hd_pack_conv1_planes': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hd_conv1_7x7s2': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_maxpool3x3s2_same': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'hd_subsample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_process_image': (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     'hd_groupnorm_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -153,6 +153,18 @@ __global__ void pack_conv1_planes_kernel(const float *__restrict__ img, uint2 *_
   lo[o] = make_uint2(l0, l1);
 }
 
+// max_pool2d(1x1, stride s) = spatial subsampling: the identity shortcut of a strided bottleneck unit (A.4).  One float4 per thread.
+__global__ void subsample_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4, int Ho, int Wo, int s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * Ho * Wo * C4) return;
+  const int c = (int)(i % C4);
+  long long r = i / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  out[i] = __ldg(in + ((size_t)((size_t)n * H + (size_t)oy * s) * W + (size_t)ox * s) * C4 + c);
+}
+
 __global__ void ief_delta_init_kernel(const float *__restrict__ theta, float *__restrict__ dst, int dst_ld, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 85) return;
@@ -235,4 +247,14 @@ extern "C" int hd_pack_conv1_planes(const float *img, void *plane_hi, void *plan
   pack_conv1_planes_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<uint2 *>(plane_hi),
                                                                                      reinterpret_cast<uint2 *>(plane_lo), N, H, W, WP);
   return hd::check_launch("pack_conv1_planes_kernel");
+}
+
+extern "C" int hd_subsample(const float *in, float *out, int N, int H, int W, int C, int stride, void *stream) {
+  HD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && stride >= 1 && hd::aligned16(in) && hd::aligned16(out),
+             "hd_subsample: bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  subsample_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N,
+                                                                             H, W, C / 4, Ho, Wo, stride);
+  return hd::check_launch("subsample_kernel");
 }

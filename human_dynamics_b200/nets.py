@@ -180,6 +180,25 @@ class PackedConv(object):
         return op
 
 
+class SubsampleOp(object):
+    """x[:, ::s, ::s, :] into a dense buffer (slim's max_pool2d(1x1, stride) shortcut): one op in a plan's op list."""
+    __slots__ = ('src', 'dst', 'geom', 'd')
+
+    def __init__(self, src, dst, n, H, C, stride):
+        self.src, self.dst, self.geom, self.d = src, dst, (n, H, H, C, stride), None
+
+    def rebind(self, field, tensor):
+        self.src = tensor
+
+    def encode_act_maps(self):
+        pass
+
+    def run(self, stream):
+        n, H, W, Cc, s = self.geom
+        check(lib.hd_subsample(fptr(self.src), fptr(self.dst), n, H, W, Cc, s, stream), 'hd_subsample')
+
+
+SUBSAMPLE_RES = os.environ.get('HD_SUBSAMPLE_RES', '1') != '0'    # A/B switch: strided identity shortcuts via hd_subsample + plain residual
 TMA_EPILOGUE = os.environ.get('HD_TMA_EPILOGUE', '1') != '0'     # A/B switch for the K <= 256 layers (results identical)
 
 
@@ -396,6 +415,12 @@ class ResNetPlan(object):
                     if ui == 0:
                         self.in_refs += [(self.ops[-1], 'in_hi', 0), (self.ops[-1], 'in_lo', 1)]
                     res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
+                elif s > 1 and SUBSAMPLE_RES:
+                    # strided identity shortcut: subsample once into a dense buffer so conv3's residual is row-aligned (TMA slab loads)
+                    self.ops.append(SubsampleOp(x, self.bufS[:n * Ho * Ho * unit['depth']], n, H, unit['depth'], s))
+                    if ui == 0:
+                        self.in_refs.append((self.ops[-1], 'res', 2))
+                    res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
                 else:
                     res, res_geom = x, (unit['depth'], H, H, s)
                 self.ops.append(unit['conv1'].bind(None, n, H, H, None, inp_split=xs, out_split=r1, impl=impl))
@@ -407,7 +432,7 @@ class ResNetPlan(object):
                 osplit = ys if nxt is not None else None
                 self.ops.append(unit['conv3'].bind(None, n, Ho, Ho, y, inp_split=r2, res=res, res_geom=res_geom, impl=impl,
                                                    out_split=osplit, post2=(nxt[0], nxt[1], 1) if nxt is not None else None))
-                if ui == 0 and 'shortcut' not in unit:
+                if ui == 0 and 'shortcut' not in unit and not (s > 1 and SUBSAMPLE_RES):
                     self.in_refs.append((self.ops[-1], 'res', 2))
                 if last:
                     self.out_split = osplit

@@ -120,6 +120,9 @@ int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *ou
  * (the first bottleneck unit's pre-activation, pre-split for the tensor-core kernel). */
 int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, const float *scale, const float *shift,
                          void *out_hi, void *out_lo, void *stream);
+/* slim's identity shortcut of a strided unit: max_pool2d(x, [1,1], stride) = x[:, ::s, ::s, :] (A.4).  in [N,H,W,C] -> out
+ * [N,ceil(H/s),ceil(W/s),C]; lets the residual of the unit's conv3 be a plain row-aligned tensor (TMA epilogue). */
+int hd_subsample(const float *in, float *out, int N, int H, int W, int C, int stride, void *stream);
 /* postnorm BN+ReLU then global mean over HxW: in [N,HW,C] -> out [N,C]. */
 int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, float *out, int N, int HW, int C, void *stream);
 

@@ -27,6 +27,14 @@ for stage, c in (('A', min(eng.config.frame_chunk, N)), ('B', min(eng.config.lat
         torch.cuda.synchronize()
     for a, b, op in evs:
         d = op.d
+        if d is None:
+            print('  (%s subsample %.3f ms)' % (stage, a.elapsed_time(b) * reps))
+            continue
+        if d.flags & 2:                   # conv1 over padded planes: report the algorithmic 7x7x3 conv, not the padded K=256 GEMM
+            M, K, Nn = d.n_img * d.Ho * d.Wo, 147, d.Cout
+            t = a.elapsed_time(b) * 1e-3 * reps
+            rows.append((t, stage, M, K, Nn, 7, 2, False, False, 2.0 * M * K * Nn * reps / t / 1e12, (d.n_img * 224 * 224 * 3 * 4 + M * Nn * 4) * reps / t / 1e9, d.impl))
+            continue
         M, K, Nn = d.n_img * d.Ho * d.Wo, d.KH * d.KW * d.Cin, d.Cout
         t = a.elapsed_time(b) * 1e-3 * reps
         fl = 2.0 * M * K * Nn * reps
