@@ -306,6 +306,11 @@ def main():
     barrier()
     t_end = sampler.mark()
     launches = int(_lib.lib.hd_launch_count())
+    # results of the LAST TIMED step for the clips / frames the oracle will check (the later end-to-end legs reuse the output buffers)
+    timed_out = None
+    if args.workload != 'smpl':
+        sel_idx = [0, B - 1]
+        timed_out = {k: last['out'][k][sel_idx].float().cpu().numpy() for k in PARITY_KEYS if k in last['out']}
     graph_nodes = None
     if args.workload != 'smpl' and args.graph and last.get('nodes'):
         graph_nodes = int(last['nodes'])
@@ -377,9 +382,9 @@ def main():
             torch.cuda.synchronize()
             worst, per = 0.0, {}
             for k in PARITY_KEYS:
-                if k not in ref or k not in last['out']:
+                if k not in ref or k not in timed_out:
                     continue
-                g = last['out'][k][sel].float().cpu().numpy().reshape(ref[k].shape).astype(np.float64)
+                g = timed_out[k].reshape(ref[k].shape).astype(np.float64)
                 e = float(np.abs(g - ref[k]).max() / max(float(np.abs(ref[k]).max()), 1e-12))
                 per[k] = e
                 worst = max(worst, e)

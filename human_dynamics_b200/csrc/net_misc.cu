@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(128) groupnorm_stats_kernel(const float *__res
 
 // process_image (src/evaluation/run_video.py:56-107): one thread per output pixel of the S x S crop.
 //   crop(y,x) = padded_scaled[y0 + y + S][x0 + x + S], padded = edge-replicated => clamp the scaled-image coordinates;
-//   scaled = cv2.resize(2*(u8/255 - 0.5), (Ws,Hs)) bilinear: source coordinate (d + 0.5)*scale - 0.5 computed in double and
-//   narrowed to float like cv2 does, floor, weights (1-f, f), neighbours clamped to the image (cv2's xofs/yofs clipping).
+//   scaled = cv2.resize(2*(u8/255 - 0.5), (Ws,Hs)) bilinear: source coordinate (d + 0.5)*scale - 0.5, floor, weights (1-f, f),
+//   neighbours clamped to the image (cv2's xofs/yofs clipping).
 __global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, int H, int W, const int4 *__restrict__ geom,
                                      float *__restrict__ out, int S, uint2 *__restrict__ plane_hi, uint2 *__restrict__ plane_lo, int WP) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,9 +105,11 @@ __global__ void process_image_kernel(const uint8_t *__restrict__ frames, int N, 
   const int Hs = g.x, Ws = g.y;
   const int xs = min(max(g.z + x, 0), Ws - 1), ys = min(max(g.w + y, 0), Hs - 1);
   const double scale_x = 1.0 / ((double)Ws / (double)W), scale_y = 1.0 / ((double)Hs / (double)H);     // cv2: scale = 1. / inv_scale
-  float fx = (float)((xs + 0.5) * scale_x - 0.5), fy = (float)((ys + 0.5) * scale_y - 0.5);
-  int sx = (int)floorf(fx), sy = (int)floorf(fy);
-  fx -= (float)sx; fy -= (float)sy;
+  // the reference resizes the float64 image: cv2 (4.x) keeps source coordinates and weights in double on that path -- probed with a
+  // ramp image, tests/test_preprocess.py -- so the fraction is taken in double and only then narrowed
+  const double cxd = (xs + 0.5) * scale_x - 0.5, cyd = (ys + 0.5) * scale_y - 0.5;
+  int sx = (int)floor(cxd), sy = (int)floor(cyd);
+  float fx = (float)(cxd - (double)sx), fy = (float)(cyd - (double)sy);
   if (sx < 0) { fx = 0.f; sx = 0; }
   if (sx >= W - 1) { fx = 0.f; sx = W - 1; }
   const int sx1 = min(sx + 1, W - 1);

@@ -74,9 +74,20 @@ def process_images(frames, bbox_params, img_size=IMG_SIZE, out=None, split_out=N
     return out, geoms
 
 
-def geometry_table(im_shape, bbox_params, img_size=IMG_SIZE):
-    """int32 [N,4] = {Hs, Ws, x0, y0} rows for hd_process_image + the per-frame info dicts."""
-    bbox_params = np.asarray(bbox_params, np.float64).reshape(-1, 3)
-    geoms = [crop_geometry(im_shape, b, img_size) for b in bbox_params]
-    g = np.array([[q['new_size'][0], q['new_size'][1], q['origin'][0], q['origin'][1]] for q in geoms], np.int32)
-    return g, geoms
+def geometry_table(im_shape, bbox_params, img_size=IMG_SIZE, with_infos=False):
+    """int32 [N,4] = {Hs, Ws, x0, y0} rows for hd_process_image -- `crop_geometry` for a whole track of same-size frames in one
+    numpy pass (same float64 formulas, same integers) -- and, on request, the per-frame info dicts."""
+    b = np.asarray(bbox_params, np.float64).reshape(-1, 3)
+    shape = np.array(im_shape[0:2])
+    new_size = np.floor(shape[None, :] * b[:, 2:3]).astype(int)                    # (N, [h, w])
+    if (new_size < 1).any():
+        raise ValueError('a bbox scale leaves an empty image')
+    factors = new_size / shape[None, :].astype(np.float64)                         # [fy, fx]
+    center_scaled = np.round(b[:, :2] * factors).astype(int) + img_size            # (x*fy, y*fx) like run_video.py:75
+    start = center_scaled - img_size // 2
+    end = center_scaled + img_size // 2
+    if (start < 0).any() or (end[:, 0] > new_size[:, 1] + 2 * img_size).any() or (end[:, 1] > new_size[:, 0] + 2 * img_size).any():
+        raise ValueError('a bbox centre is more than one crop away from the frame: the reference yields a ragged crop')
+    g = np.concatenate([new_size, start - img_size], axis=1).astype(np.int32)      # Hs, Ws, x0, y0
+    infos = [crop_geometry(im_shape, bb, img_size) for bb in b] if with_infos else None
+    return g, infos

@@ -68,8 +68,10 @@ def test_c3_chunking_does_not_change_results(c3, weights, smpl_model):
     eng2 = HMMREngine(weights, smpl_model, HMMRConfig(batch_size=B, sequence_length=T, frame_chunk=16, late_chunk=32))
     o2 = eng2.predict(torch.from_numpy(img[:B]).cuda())
     torch.cuda.synchronize()
-    for k in ('omegas', 'verts', 'kps', 'verts_delta'):
+    for k in ('omegas', 'omegas_delta', 'cams', 'shapes'):          # everything up to the IEF output: bit-identical
         assert torch.equal(o2[k], out[k][:B]), k
+    for k in ('verts', 'kps', 'verts_delta'):                       # SMPL picks its kernel by batch size (80 vs 640 poses): same numbers to 1e-5
+        assert rel_err(o2[k].cpu().numpy(), out[k][:B].cpu().numpy()) < 2e-5, k
 
 
 def test_c2_single_frame_batch64(weights, smpl_model):
@@ -255,12 +257,13 @@ def test_tester_host_paths_numpy_and_uint8_frames(weights, smpl_model):
         assert np.array_equal(got_u8[k], dev[k]), k
     # (3) a plain (pageable) numpy array of crops through Tester.predict: page-locked in place, same numbers
     crops_np = crops.cpu().numpy().reshape(B, T, 224, 224, 3).copy()
+    n_reg = len(tester._registered)                    # (the uint8 frame array of step (1) is registered already)
     got_np = tester.predict(crops_np)
-    assert len(tester._registered) == 1
+    assert len(tester._registered) == n_reg + 1
     for k in dev:
         assert np.array_equal(got_np[k], dev[k]), k
     again = tester.predict(crops_np)                   # same buffer: no second registration, next ring slot
-    assert len(tester._registered) == 1 and again['verts'] is not got_np['verts']
+    assert len(tester._registered) == n_reg + 1 and again['verts'] is not got_np['verts']
     assert np.array_equal(again['verts'], got_np['verts'])
     # (4) against the reference restatement end to end (cv2 process_image -> oracle graph), clip 0
     ref_crops = np.stack([preproc_ref.process_image(frames[0, t], boxes[0, t])['image'] for t in range(T)]).astype(np.float32)
