@@ -11,8 +11,9 @@
 // the result in the same staging slot; the CTA then writes 16 x 1536 contiguous bytes with 8-byte vector stores.
 // HBM traffic = read v_posed + write verts; W tile and the A12 operand blocks (75 MB for 65536 poses) live in smem / L2.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (vertex rows), warp 4 operand loader (cp.async, 128B-swizzled K-major tiles),
-// warp 5 TMEM allocator + MMA issuer.  Persistent: CTA c walks a contiguous range of the (vertex tile, pose batch) list.
+// Warp roles (320 threads): warps 0-7 epilogue (thread = vertex row; warps 0-3 take poses 0-7 of a batch, warps 4-7 poses 8-15,
+// two warps per scheduler hide each other's TMEM / shared-memory latency), warp 8 operand loader (cp.async, 128B-swizzled
+// K-major tiles), warp 9 TMEM allocator + MMA issuer.  Persistent: CTA c walks a contiguous range of the (vertex tile, pose batch) list.
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,7 +35,7 @@ constexpr int LBS_SMEM = OFF_BAR + 128 + 1024;
 constexpr uint32_t LBS_IDESC = (1u << 4) | ((uint32_t)(LN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // f16 x f16 -> f32, M=128, N=256
 constexpr int TMEM_COLS = 512;                  // 2 accumulators of 256 columns
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w_lo,          // [Vpad, 32]
                    const __half *__restrict__ a_hi, const __half *__restrict__ a_lo,          // [N, 12, 32]
                    const float *__restrict__ v_posed, long long vp_ld, float *__restrict__ verts, int N, int V, int out_mul,
@@ -64,12 +65,12 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
       mbar_init(full_bar(s), 32);
       mbar_init(empty_bar(s), 1);
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     mbar_init(w_bar, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -78,7 +79,7 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =============================== operand loader ===============================
     int cur_vt = -1;
     for (int q = 0; q < my; ++q) {
@@ -118,7 +119,7 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
     }
     cp_async_commit();
     cp_async_wait<0>();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       int cur_vt = -1;
@@ -153,22 +154,26 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
       }
     }
   } else {
-    // =============================== epilogue: thread = vertex ===============================
-    const int t = threadIdx.x;                                      // 0..127 = TMEM lane = vertex row of the tile
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // =============================== epilogue: thread = vertex, two groups of 8 poses ===============================
+    const int tid = threadIdx.x;                                    // 0..255
+    const int t = tid & 127;                                        // TMEM lane = vertex row of the tile
+    const int half = tid >> 7;                                      // poses half*8 .. half*8+7 of the batch
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int vgrp = tid / 96, vj = tid - vgrp * 96;                // v_posed staging: threads 0..191 = 2 groups x 96 chunks of a pose row
     auto issue_vp = [&](int q) {                                    // v_posed rows of batch q -> staging buffer q & 1
-      if (q < my) {
+      if (q < my && vgrp < 2) {
         const long long w = w0 + q;
         const int vt = (int)(w / n_batches), pb = (int)(w % n_batches);
         const uint32_t dst = smem_base + OFF_VP + (q & 1) * VP_STAGE;
         const int nv = (V - vt * 128) < 128 ? (V - vt * 128) : 128;
         const int chunks = (nv * 3 + 3) / 4;                        // 16-byte chunks per pose row (<= 96; reads stay inside the padded row)
-        for (int c = t; c < LP * 96; c += 128) {
-          const int p = c / 96, j = c % 96;
+        const float *src0 = v_posed + (size_t)vt * 384 + vj * 4;
+#pragma unroll
+        for (int i = 0; i < LP / 2; ++i) {
+          const int p = vgrp * (LP / 2) + i;
           const int n = pb * LP + p;
-          const bool ok = n < N && j < chunks;
-          const float *src = v_posed + (size_t)(ok ? n : 0) * vp_ld + (size_t)vt * 384 + (ok ? j * 4 : 0);
-          cp_async16(dst + (uint32_t)(p * VP_ROW + j * 16), src, ok ? 16u : 0u);
+          const bool ok = n < N && vj < chunks;
+          cp_async16(dst + (uint32_t)(p * VP_ROW + vj * 16), ok ? src0 + (size_t)n * vp_ld : v_posed, ok ? 16u : 0u);
         }
       }
       cp_async_commit();                                            // one (possibly empty) group per call keeps the wait counts uniform
@@ -181,45 +186,53 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
       const int s = q & 1;
       const uint32_t u = (uint32_t)(q >> 1);
       cp_async_wait<1>();                                           // this thread's copies of batch q have landed (batch q+1 may be in flight)
-      named_bar_sync(1, 128);                                       // ... and everybody else's
+      named_bar_sync(1, 256);                                       // ... and everybody else's
       mbar_wait(tfull_bar(s), u & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float *stage = reinterpret_cast<float *>(smem + OFF_VP + s * VP_STAGE);
       const int np = (N - pb * LP) < LP ? (N - pb * LP) : LP;
-#pragma unroll 4
-      for (int p = 0; p < LP; ++p) {
-        uint32_t T[16];
-        tmem_ld16(tmem + lane_off + (uint32_t)(s * 256 + p * 16), T);      // 12 entries of this vertex's transform for pose p (+4 unused)
-        float *vp = stage + p * 384 + t * 3;
-        const float x = vp[0], y = vp[1], z = vp[2];
-        vp[0] = __uint_as_float(T[0]) * x + __uint_as_float(T[1]) * y + __uint_as_float(T[2]) * z + __uint_as_float(T[3]);
-        vp[1] = __uint_as_float(T[4]) * x + __uint_as_float(T[5]) * y + __uint_as_float(T[6]) * z + __uint_as_float(T[7]);
-        vp[2] = __uint_as_float(T[8]) * x + __uint_as_float(T[9]) * y + __uint_as_float(T[10]) * z + __uint_as_float(T[11]);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {                                 // 4 poses per TMEM round trip
+        uint32_t T[4][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_ld16_nowait(tmem + lane_off + (uint32_t)(s * 256 + (half * 8 + g * 4 + i) * 16), T[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float *vp = stage + (half * 8 + g * 4 + i) * 384 + t * 3;
+          const float x = vp[0], y = vp[1], z = vp[2];
+          const float *Tf = reinterpret_cast<const float *>(T[i]);
+          vp[0] = Tf[0] * x + Tf[1] * y + Tf[2] * z + Tf[3];
+          vp[1] = Tf[4] * x + Tf[5] * y + Tf[6] * z + Tf[7];
+          vp[2] = Tf[8] * x + Tf[9] * y + Tf[10] * z + Tf[11];
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(s));
-      named_bar_sync(1, 128);                                       // all 128 result rows of the batch are in the staging buffer
+      named_bar_sync(1, 256);                                       // all result rows of the batch are in the staging buffer
       // coalesced write-out: per pose 128 vertices x 12 B = 1536 contiguous bytes (8-byte aligned for every pose slot)
       const int nv = (V - vt * 128) < 128 ? (V - vt * 128) : 128;
-      const int units = (nv * 3) / 2;                               // 8-byte units per pose row (nv * 3 floats; nv*3 is even for nv = 128 and 106)
-      const int odd = (nv * 3) & 1;
-      for (int c = t; c < np * 192; c += 128) {
-        const int p = c / 192, j = c % 192;
-        const int n = pb * LP + p;
-        float *dst = verts + ((size_t)n * out_mul + out_off) * ((size_t)V * 3) + (size_t)vt * 384;
-        const float *src = stage + p * 384;
-        if (j < units) *reinterpret_cast<float2 *>(dst + 2 * j) = *reinterpret_cast<const float2 *>(src + 2 * j);
-        else if (odd && j == units) dst[2 * j] = src[2 * j];
+      const int units = (nv * 3) / 2;                               // 8-byte units per pose row
+      const bool odd = ((nv * 3) & 1) != 0;
+      if (tid < 192) {
+        float *dst = verts + ((size_t)(pb * LP) * out_mul + out_off) * ((size_t)V * 3) + (size_t)vt * 384 + 2 * tid;
+        const size_t dstep = (size_t)out_mul * ((size_t)V * 3);
+        const float *src = stage + 2 * tid;
+        for (int p = 0; p < np; ++p) {
+          if (tid < units) *reinterpret_cast<float2 *>(dst) = *reinterpret_cast<const float2 *>(src);
+          else if (odd && tid == units) dst[0] = src[0];
+          dst += dstep; src += 384;
+        }
       }
-      named_bar_sync(1, 128);                                       // staging buffer s is free again
+      named_bar_sync(1, 256);                                       // staging buffer s is free again
       issue_vp(q + 2);
     }
     cp_async_wait<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
@@ -248,7 +261,7 @@ extern "C" int hd_smpl_lbs_tc(const void *w_hi, const void *w_lo, const void *a1
   }
   const long long total = (long long)((V + 127) / 128) * ((N + hd::LP - 1) / hd::LP);
   const int grid = (int)(total < num_sms[dev] ? total : num_sms[dev]);
-  hd::smpl_lbs_tc_kernel<<<grid, 192, hd::LBS_SMEM, (cudaStream_t)stream>>>(
+  hd::smpl_lbs_tc_kernel<<<grid, 320, hd::LBS_SMEM, (cudaStream_t)stream>>>(
       reinterpret_cast<const __half *>(w_hi), reinterpret_cast<const __half *>(w_lo), reinterpret_cast<const __half *>(a12t_hi),
       reinterpret_cast<const __half *>(a12t_lo), v_posed, vp_ld, verts, N, V, out_mul, out_off);
   return hd::check_launch("smpl_lbs_tc_kernel");
