@@ -168,6 +168,7 @@ def main():
     ap.add_argument('--frame-chunk', type=int, default=int(os.environ.get('HD_FRAME_CHUNK', '160')))
     ap.add_argument('--late-chunk', type=int, default=int(os.environ.get('HD_LATE_CHUNK', '640')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the C2 / C5 sub-results of the default line')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('HD_GRAPH', '1')),
                     help='1 = replay the device-resident step from a CUDA graph (one graph launch per step), 0 = eager launches')
     args = ap.parse_args()
@@ -397,6 +398,11 @@ def main():
         ok = all(torch.equal(last['g'][k][:B], last['out'][k]) for k in gather_keys)
         parity = {'gather_own_shard_bit_identical': bool(ok)}
 
+    # ------------------------------------------------------------------ the other single-GPU BASELINE configs, device-resident
+    extra = None
+    if rank == 0 and world == 1 and args.workload == 'hmmr' and not args.no_extra:
+        extra = measure_extra_configs(args, peaks, w, smpl, dev)
+
     if rank == 0:
         line = {'metric': metric, 'value': value, 'unit': unit_name, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -418,6 +424,8 @@ def main():
             line['roofline'] = roofline
         if cpu_baseline:
             line['cpu_baseline'] = cpu_baseline
+        if extra:
+            line['extra'] = extra
         if parity:
             line['parity'] = parity
             if 'parity_max_rel' in parity:
@@ -440,6 +448,56 @@ def workload_name(args):
     if args.workload == 'single_frame':
         return 'BASELINE configs[1]: single-frame ResNet-50 + 3-iter IEF + SMPL, batch 64'
     return 'BASELINE configs[4]: SMPL LBS microbench, 65536 poses -> 6890 verts'
+
+
+def measure_extra_configs(args, peaks, w, smpl, dev):
+    """BASELINE configs[1] (single-frame, batch 64) and configs[4] (SMPL LBS microbench, 65536 poses) timed device-resident with
+    CUDA events so that the default bench line carries them too (same code as --workload single_frame / smpl)."""
+    import torch
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from human_dynamics_b200.engine import HMMREngine
+    from human_dynamics_b200.smpl import SMPLConstants
+    out = {}
+
+    def timed(fn, steps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    # C2
+    n = 64
+    eng = HMMREngine(w, smpl, HMMRConfig(batch_size=n, sequence_length=1), device=dev, impl=args.mode)
+    img = torch.from_numpy(synthetic.make_images(n, seed=300)).to(dev).view(n, 1, 224, 224, 3)
+    ms = timed(lambda: eng.predict_graphed(img, single_frame=True) if args.graph else eng.predict(img, single_frame=True), 10)
+    fl = n * (FLOP_RESNET_FRAME + FLOP_IEF_FRAME_3HEADS / 3 + FLOP_SMPL_POSE)
+    out['C2_single_frame_batch64'] = {'value': n / (ms * 1e-3), 'unit': 'frames/sec', 'ms_per_step': ms,
+                                      'roofline': {'bound': 'tensor', 'achieved': fl / (ms * 1e-3) / 1e12, 'peak': peaks['bf16_tflops_sustained'],
+                                                   'unit': 'TFLOP/s', 'frac': fl / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained']},
+                                      'note': 'one 64-frame pass: 49..392 tiles per late layer on 148 SMs (wave quantisation), L2-resident inputs'}
+    del eng
+    # C5
+    N = 65536
+    consts = SMPLConstants(smpl, device=dev)
+    beta, theta = synthetic.make_smpl_inputs(N, seed=0)
+    b_d, t_d = torch.from_numpy(beta).to(dev), torch.from_numpy(theta).to(dev)
+    cam = torch.ones((N, 3), device=dev)
+    outs = consts.forward(b_d, t_d, cam=cam)
+    ms = timed(lambda: consts.forward(b_d, t_d, cam=cam, out=outs), 5)
+    ach = N * BYTES_SMPL_POSE / (ms * 1e-3) / 1e9
+    out['C5_smpl_lbs_65536'] = {'value': N / (ms * 1e-3), 'unit': 'poses/sec', 'ms_per_step': ms,
+                                'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                                             'algorithmic_bytes_per_step': N * BYTES_SMPL_POSE},
+                                'note': 'pose + blend GEMM (tcgen05, 3 MMAs per product in the parity mode: %.1f TFLOP-equivalents, the '
+                                        'tensor pipe bounds this config before HBM does) + tensor-core skinning + keypoints' % (N * 256 * 20672 * 2 * 3 / 1e12)}
+    del outs, consts
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure_roofline(args, peaks, env):
