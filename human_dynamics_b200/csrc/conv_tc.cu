@@ -46,7 +46,8 @@ struct Cfg {
   // DUAL (epilogue-bound layers, K <= 256, one drain group per tile): two drain/epilogue warp groups take alternate tiles;
   // the main loop is short there, so 2 operand stages suffice and pay for the second set of staging tiles.
   static constexpr int STAGES = (DUAL || TEPI) ? 2 : 3;
-  static constexpr int DW = DUAL ? 8 : 4;                       // drain + epilogue warps
+  static constexpr int DW = (DUAL || TEPI) ? 8 : 4;             // drain + epilogue warps (DUAL: two groups on alternate tiles;
+                                                                // TEPI: two groups on alternate 32-column slabs of the same tile)
   static constexpr int NUM_THREADS = (DW + 8 + 4) * 32;         // + 8 producer warps + {TMA, MMA, 2 idle}
   static constexpr int BKE = HALF ? 64 : 32;                    // K elements per chunk (one 128-byte row)
   static constexpr int B_TILE_BYTES = BN * 128;
@@ -88,6 +89,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   using C = Cfg<BN, HALF, DUAL, TEPI>;
   constexpr int BKE = C::BKE, PF = C::PF, V = C::V, STAGES = C::STAGES, DW = C::DW, NUM_THREADS = C::NUM_THREADS;
   constexpr int W_TMA = DW + 8, W_MMA = DW + 9;
+  constexpr int W_RES = DW + 10, W_ST = DW + 11;      // TEPI: residual-load agent, store agent (idle warps otherwise)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -98,7 +100,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };    // accumulator b drained
   auto smallf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };  // cross-term accumulator b drained
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
-  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };     // TEPI: residual slab landed in ring buffer b
+  // TEPI staging ring (the gap up to EPI_OFFSET holds these): residual slab landed in buffer b / slab b computed and written by the
+  // 128 drain threads / the TMA stores of buffer b have read it
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };
+  auto ready_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 10 + b); };
+  auto free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 13 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (GATHER ? p.K_pad : p.K) / BKE;   // GATHER: ragged Cin (conv1: K=147 zero-padded to 192)
@@ -115,11 +121,15 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);     // tcgen05.commit
-      mbar_init(acce_bar(b), 4);     // one lane per drain warp
-      mbar_init(smallf_bar(b), 4);
+      mbar_init(acce_bar(b), TEPI ? 8 : 4);     // one lane per drain warp that reads the accumulator
+      mbar_init(smallf_bar(b), TEPI ? 8 : 4);
     }
     if (TEPI)
-      for (int b = 0; b < C::EPI_NB; ++b) mbar_init(res_bar(b), 1);
+      for (int b = 0; b < C::EPI_NB; ++b) {
+        mbar_init(res_bar(b), 1);
+        mbar_init(ready_bar(b), 128);
+        mbar_init(free_bar(b), 1);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_TMA) {
@@ -135,8 +145,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 
   if (warp >= DW && warp < DW + 8) {
     // =============================== A producers (256 threads) ===============================
-    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    else if (TEPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (DUAL || TEPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int t = threadIdx.x - DW * 32;  // 0..255
     const int j = t & 7;                  // 16-byte chunk within the 128-byte K row
@@ -336,38 +345,23 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   } else if (warp < DW) {
     // =============================== drain + epilogue ===============================
     const int dgroup = warp >> 2, quarter = warp & 3;     // DUAL: group 0 takes even tiles, group 1 odd tiles
-    if (DUAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    else if (TEPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (DUAL || TEPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_wait = 0, t_epi = 0, t_start = prof ? clock64() : 0;
     float *stg0 = reinterpret_cast<float *>(smem + C::STG_OFFSET) + warp * (C::NSTG * 32 * C::STG_LD);
     const int hw = p.Ho * p.Wo;
-    // ---- TEPI: residual slab loads run one slab ahead of the math, issued by the group leader (thread 0) ----
-    const bool epi_leader = threadIdx.x == 0;
-    auto epi_issue_res = [&](int j) {          // residual of global slab j (tile j / NSL of this CTA, slab j % NSL) -> ring buffer j % NB
-      constexpr int NSLq = BN / 32;
-      const int tj = j / NSLq;
-      if (tj >= my_tiles) return;
-      const int tile = (int)blockIdx.x + tj * (int)gridDim.x;
-      const int b = j % C::EPI_NB;
-      mbar_arrive_expect_tx(res_bar(b), C::EPI_F32_BYTES);
-      tma_load_2d(smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES, &em.res, res_bar(b), (tile % tiles_n) * BN + (j % NSLq) * 32,
-                  (tile / tiles_n) * BM);
-    };
-    if (TEPI && epi_leader && p.res) epi_issue_res(0);
-    for (int ti = dgroup; ti < my_tiles; ti += (DUAL ? 2 : 1)) {
+    // TEPI: both groups work on every tile; group g owns the 32-column slabs g, g+2, ... (sums[] holds only those columns)
+    constexpr int SN = TEPI ? BN / 2 : BN;
+    auto sum_col = [&](int i) { return TEPI ? ((i >> 5) * 2 + dgroup) * 32 + (i & 31) : i; };     // accumulator column of sums[i]
+    for (int ti = (DUAL ? dgroup : 0); ti < my_tiles; ti += (DUAL ? 2 : 1)) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      float sums[BN];
+      float sums[SN];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) sums[i] = 0.f;
+      for (int i = 0; i < SN; ++i) sums[i] = 0.f;
       if (TEPI) {
-        if (epi_leader && p.res && ti + 1 < my_tiles) {      // next tile's residual slabs -> L2, a whole tile period ahead
-          const int tilen = (int)blockIdx.x + (ti + 1) * (int)gridDim.x;
-          for (int sl = 0; sl < BN / 32; ++sl) tma_prefetch_2d(&em.res, (tilen % tiles_n) * BN + sl * 32, (tilen / tiles_n) * BM);
-        }
       } else if (p.res && p.vec_out) {       // pull the residual rows of this group's NEXT tile towards L2 (a whole tile period of lead
                                       // time; the very first tile is prefetched on entry), so the epilogue's cp.asyncs hit L2
         const int tstep = DUAL ? 2 : 1;
@@ -396,9 +390,9 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         if (prof) t_wait += clock64() - tw0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {       // x16 loads: 16 live temporaries next to the BN running sums
+        for (int c0 = 0; c0 < SN; c0 += 16) {       // x16 loads: 16 live temporaries next to the running sums
           uint32_t v[16];
-          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * (2 + b) + c0), v);
+          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * (2 + b) + sum_col(c0)), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) sums[c0 + i] += __uint_as_float(v[i]);     // round-to-nearest fp32 adds
         }
@@ -409,9 +403,9 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       if (SPLIT) {      // the tile's last accf commit also covers every cross-term MMA of the tile
         const int sb = ti & 1;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 0; c0 < SN; c0 += 16) {
           uint32_t v[16];
-          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * sb + c0), v);
+          tmem_ld16(tmem_d + lane_off + (uint32_t)(BN * sb + sum_col(c0)), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) sums[c0 + i] += __uint_as_float(v[i]) * (HALF ? (1.0f / 2048.0f) : 1.0f);
         }
@@ -555,23 +549,22 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
       } else {
-        // ---- TMA epilogue: thread = accumulator row (TMEM lane); per 32-column slab: wait for the residual slab (TMA load,
-        // issued one slab ahead), v = acc*scale + shift (+ residual) (ReLU) in place in the swizzled staging buffer, the next
-        // layer's pre-activated fp16 head/remainder beside it, then one thread hands the three slabs to TMA stores. ----
+        // ---- TMA epilogue: thread = accumulator row (TMEM lane); per 32-column slab: wait for the residual slab (TMA load by the
+        // residual agent, up to two slabs ahead), v = acc*scale + shift (+ residual) (ReLU) in place in the swizzled staging
+        // buffer, the next layer's pre-activated fp16 head/remainder beside it, then arrive on the slab's `ready` barrier: the store
+        // agent hands the three slabs to TMA stores and recycles the buffer.  No thread of this group ever waits for a store. ----
         constexpr int NSL = BN / 32, NB = C::EPI_NB;
         const int row = quarter * 32 + lane;
         const uint32_t sw128 = (uint32_t)(row & 7), sw64 = (uint32_t)((row >> 1) & 3);
         const bool has_res = p.res != nullptr, has_o32 = p.out != nullptr, has_o16 = p.out_hi != nullptr;
 #pragma unroll
-        for (int sl = 0; sl < NSL; ++sl) {
-          const int gi = ti * NSL + sl;                 // running slab index of this CTA
+        for (int s2 = 0; s2 < NSL / 2; ++s2) {
+          const int sl = s2 * 2 + dgroup;               // this group's slabs: dgroup, dgroup + 2
+          const int gi = ti * NSL + sl;                 // running slab index of this CTA (the agents walk them in this order)
           const int b = gi % NB;
           uint8_t *buf = smem + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
-          if (epi_leader) {
-            bulk_wait_read<NB - 2>();                   // the stores of slab gi-2 have read their buffer = buffer (gi+1) % NB
-            if (has_res) epi_issue_res(gi + 1);
-          }
-          if (has_res) mbar_wait(res_bar(b), (uint32_t)(gi / NB) & 1u);
+          if (has_res) mbar_wait(res_bar(b), (uint32_t)(gi / NB) & 1u);              // residual landed (=> buffer was free)
+          else mbar_wait(free_bar(b), ((uint32_t)(gi / NB) & 1u) ^ 1u);             // stores of slab gi - NB have read the buffer
           uint8_t *frow = buf + row * 128;
           uint8_t *hrow = buf + C::EPI_F32_BYTES + row * 64;
           uint8_t *lrow = hrow + C::EPI_H_BYTES;
@@ -584,7 +577,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int c = 2 * h + q;
-              float4 v = make_float4(sums[sl * 32 + 4 * c], sums[sl * 32 + 4 * c + 1], sums[sl * 32 + 4 * c + 2], sums[sl * 32 + 4 * c + 3]);
+              float4 v = make_float4(sums[s2 * 32 + 4 * c], sums[s2 * 32 + 4 * c + 1], sums[s2 * 32 + 4 * c + 2], sums[s2 * 32 + 4 * c + 3]);
               if (p.post_scale) {
                 const float4 s = __ldg(reinterpret_cast<const float4 *>(p.post_scale + cb + 4 * c));
                 v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
@@ -629,16 +622,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the TMA store
-          named_bar_sync(1, 128);
-          if (epi_leader) {
-            const uint32_t sb = smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
-            if (has_o32 && slab_ok) tma_store_2d(&em.out, sb, cb, m0);
-            if (has_o16 && slab_ok) {
-              tma_store_2d(&em.ohi, sb + C::EPI_F32_BYTES, cb, m0);
-              tma_store_2d(&em.olo, sb + C::EPI_F32_BYTES + C::EPI_H_BYTES, cb, m0);
-            }
-            bulk_commit();
-          }
+          mbar_arrive(ready_bar(b));
         }
       }
       if (prof) t_epi += clock64() - te0;
@@ -647,7 +631,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   } else {
     // register pool = threads x launch allocation (512 x 128, or 640 x 96 for DUAL); the budgets below must fit in it or
     // setmaxnreg.inc never returns:  4-warp: 128*200 + 256*136 + 128*40 = 65536;  DUAL: 256*192 + 256*32 + 128*24 = 60416 <= 61440
-    if (DUAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (DUAL || TEPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == W_TMA) {
       // =============================== B producer (TMA) ===============================
@@ -672,6 +656,49 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           }
         }
         if (prof) { p.dbg[8] = clock64() - t_start; p.dbg[9] = t_wait; }
+      }
+    } else if (TEPI && warp == W_RES) {
+      // =============================== TEPI: residual-load agent ===============================
+      if (lane == 0 && p.res) {
+        constexpr int NSL = BN / 32, NB = C::EPI_NB;
+        const int total = my_tiles * NSL;
+        for (int j = 0; j < total; ++j) {
+          const int tj = j / NSL, sl = j - tj * NSL;
+          const int tile = (int)blockIdx.x + tj * (int)gridDim.x;
+          const int c0 = (tile % tiles_n) * BN + sl * 32, c1 = (tile / tiles_n) * BM;
+          const int b = j % NB;
+          if (tj + 1 < my_tiles) {                 // the same slab of the NEXT tile -> L2, a whole tile period ahead
+            const int tilen = tile + (int)gridDim.x;
+            tma_prefetch_2d(&em.res, (tilen % tiles_n) * BN + sl * 32, (tilen / tiles_n) * BM);
+          }
+          mbar_wait(free_bar(b), ((uint32_t)(j / NB) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(res_bar(b), C::EPI_F32_BYTES);
+          tma_load_2d(smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES, &em.res, res_bar(b), c0, c1);
+        }
+      }
+    } else if (TEPI && warp == W_ST) {
+      // =============================== TEPI: store agent ===============================
+      if (lane == 0) {
+        constexpr int NSL = BN / 32, NB = C::EPI_NB;
+        const int total = my_tiles * NSL;
+        for (int j = 0; j < total; ++j) {
+          const int tj = j / NSL, sl = j - tj * NSL;
+          const int tile = (int)blockIdx.x + tj * (int)gridDim.x;
+          const int c0 = (tile % tiles_n) * BN + sl * 32, c1 = (tile / tiles_n) * BM;
+          const int b = j % NB;
+          mbar_wait(ready_bar(b), (uint32_t)(j / NB) & 1u);
+          const uint32_t sb = smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
+          if (c0 < p.Cout) {
+            if (p.out) tma_store_2d(&em.out, sb, c0, c1);
+            if (p.out_hi) {
+              tma_store_2d(&em.ohi, sb + C::EPI_F32_BYTES, c0, c1);
+              tma_store_2d(&em.olo, sb + C::EPI_F32_BYTES + C::EPI_H_BYTES, c0, c1);
+            }
+          }
+          bulk_commit();
+          bulk_wait_read<0>();                     // only this agent waits for the TMA engine; then the buffer goes back into the ring
+          mbar_arrive(free_bar(b));
+        }
       }
     } else if (warp == W_MMA) {
       // =============================== MMA issuer ===============================
@@ -729,7 +756,6 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     }
   }
-  if (TEPI && threadIdx.x == 0) bulk_wait_read<0>();     // the last TMA stores have read their staging buffers
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == W_TMA) {

@@ -164,6 +164,7 @@ def test_batch_rot2aa_matches_oracle():
     aa = batch_rot2aa(R).cpu().numpy()
     ref = smpl_ref.batch_rot2aa(R.cpu().numpy().astype(np.float64), np.float64)
     assert np.abs(aa - ref).max() < 5e-4          # acos near 1 amplifies fp32 rounding of the trace
-    big = np.linalg.norm(th, axis=1) > 0.3
+    nrm = np.linalg.norm(th, axis=1)
+    big = (nrm > 0.3) & (nrm < 3.0)                  # beyond pi the axis-angle vector of the same rotation is a different one
     assert np.abs(aa[big] - th[big]).max() < 2e-5
     assert np.all(aa[::50] == 0.0)
