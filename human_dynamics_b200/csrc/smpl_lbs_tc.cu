@@ -11,9 +11,9 @@
 // the result in the same staging slot; the CTA then writes 16 x 1536 contiguous bytes with 8-byte vector stores.
 // HBM traffic = read v_posed + write verts; W tile and the A12 operand blocks (75 MB for 65536 poses) live in smem / L2.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (thread = vertex row; warps 0-3 take poses 0-7 of a batch, warps 4-7 poses 8-15,
-// two warps per scheduler hide each other's TMEM / shared-memory latency), warp 8 operand loader (cp.async, 128B-swizzled
-// K-major tiles), warp 9 TMEM allocator + MMA issuer.  Persistent: CTA c walks a contiguous range of the (vertex tile, pose batch) list.
+// Warp roles (416 threads): warps 0-7 epilogue (thread = vertex row; warps 0-3 take poses 0-7 of a batch, warps 4-7 poses 8-15,
+// two warps per scheduler hide each other's TMEM / shared-memory latency), warps 8-11 operand loaders (cp.async into
+// 128B-swizzled K-major tiles, per-lane offsets precomputed), warp 12 TMEM allocator + MMA issuer.  Persistent (see WorkIter).
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,7 +35,39 @@ constexpr int LBS_SMEM = OFF_BAR + 128 + 1024;
 constexpr uint32_t LBS_IDESC = (1u << 4) | ((uint32_t)(LN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // f16 x f16 -> f32, M=128, N=256
 constexpr int TMEM_COLS = 512;                  // 2 accumulators of 256 columns
 
-__global__ void __launch_bounds__(320, 1)
+constexpr int RUN = 64;                         // consecutive pose batches of one vertex tile handled by one CTA before it moves on
+
+// Work order.  Items are (vertex tile, pose batch); they are grouped into runs of RUN consecutive batches of one vertex tile, the
+// runs are ordered pose-block-major ([pose block][vertex tile]) and dealt round-robin to the CTAs.  All CTAs therefore sweep the
+// pose dimension together: at any moment the chip touches a window of ~3 * RUN * 16 poses of the A12 operand (a few MB, L2-hot,
+// read by all 54 vertex tiles) while v_posed / verts stream through once; the W tile is reloaded once per run.
+struct WorkIter {
+  int n_batches, n_vt, total_runs, run, k, nb, vt, pb0;
+  __device__ WorkIter(int N, int V, int first_run) {
+    n_batches = (N + LP - 1) / LP;
+    n_vt = (V + 127) / 128;
+    total_runs = ((n_batches + RUN - 1) / RUN) * n_vt;
+    run = first_run;
+    k = 0;
+    load();
+  }
+  __device__ void load() {
+    if (run < total_runs) {
+      const int sb = run / n_vt;
+      vt = run - sb * n_vt;
+      pb0 = sb * RUN;
+      nb = (n_batches - pb0) < RUN ? (n_batches - pb0) : RUN;
+    }
+  }
+  __device__ bool valid() const { return run < total_runs; }
+  __device__ int pb() const { return pb0 + k; }
+  __device__ bool first_of_run() const { return k == 0; }
+  __device__ void next(int stride) {
+    if (++k == nb) { k = 0; run += stride; load(); }
+  }
+};
+
+__global__ void __launch_bounds__(416, 1)
 smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w_lo,          // [Vpad, 32]
                    const __half *__restrict__ a_hi, const __half *__restrict__ a_lo,          // [N, 12, 32]
                    const float *__restrict__ v_posed, long long vp_ld, float *__restrict__ verts, int N, int V, int out_mul,
@@ -44,33 +76,27 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar = smem_base + OFF_BAR;
-  auto full_bar = [&](int s) { return bar + 8u * s; };            // B operands of stage s landed (32 loader lanes)
+  auto full_bar = [&](int s) { return bar + 8u * s; };            // B operands of stage s landed (128 loader lanes)
   auto empty_bar = [&](int s) { return bar + 8u * (2 + s); };     // MMAs that read stage s (and the W tile) completed
   auto tfull_bar = [&](int s) { return bar + 8u * (4 + s); };     // accumulator s complete
-  auto tempty_bar = [&](int s) { return bar + 8u * (6 + s); };    // accumulator s drained (4 epilogue warps)
+  auto tempty_bar = [&](int s) { return bar + 8u * (6 + s); };    // accumulator s drained (8 epilogue warps)
   const uint32_t w_bar = bar + 8u * 8;                            // W tile landed
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 8 * 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_batches = (N + LP - 1) / LP;
-  const int n_vt = (V + 127) / 128;
-  const long long total = (long long)n_vt * n_batches;
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  const long long w0 = (long long)blockIdx.x * per;
-  const long long w1 = (w0 + per < total) ? w0 + per : total;
-  const int my = w1 > w0 ? (int)(w1 - w0) : 0;
+  constexpr int W_LOAD = 8, W_MMA = 12;                           // warps 0-7 epilogue, 8-11 loaders, 12 MMA + TMEM allocator
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(full_bar(s), 32);
+      mbar_init(full_bar(s), 128);
       mbar_init(empty_bar(s), 1);
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);
     }
-    mbar_init(w_bar, 32);
+    mbar_init(w_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -79,22 +105,31 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
-    // =============================== operand loader ===============================
-    int cur_vt = -1;
-    for (int q = 0; q < my; ++q) {
-      const long long w = w0 + q;
-      const int vt = (int)(w / n_batches), pb = (int)(w % n_batches);
+  if (warp >= W_LOAD && warp < W_MMA) {
+    // =============================== operand loaders (128 lanes) ===============================
+    const int lt = threadIdx.x - W_LOAD * 32;
+    // this lane's 6 chunk pairs of a B block (16 poses x 12 entries x 4 chunks of 16 B) and 4 of the W tile: constant per lane
+    uint32_t b_soff[6], b_goff[6], b_pose[6];
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int c = it * 128 + lt, g = c >> 2, j = c & 3;
+      const int p = g / 12, i = g - p * 12, r = p * 16 + i;       // smem row: 16 per pose
+      b_soff[it] = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+      b_goff[it] = (uint32_t)(g * 32 + j * 8);                     // halves from the start of the batch's contiguous block
+      b_pose[it] = (uint32_t)p;
+    }
+    int q = 0;
+    for (WorkIter wi(N, V, blockIdx.x); wi.valid(); wi.next(gridDim.x), ++q) {
       const int s = q & 1;
       const uint32_t u = (uint32_t)(q >> 1);
       mbar_wait(empty_bar(s), (u & 1u) ^ 1u);                       // MMAs of batch q-2 have read stage s
-      if (vt != cur_vt) {
+      if (wi.first_of_run()) {
         // new vertex tile: every earlier MMA (they read the W tile) must have completed before it is overwritten
         if (q >= 1) mbar_wait(empty_bar((q - 1) & 1), ((uint32_t)((q - 1) >> 1)) & 1u);
-        cur_vt = vt;
-        for (int c = lane; c < 128 * 4; c += 32) {                 // 128 rows x 4 chunks of 16 B (32 fp16 of K)
-          const int r = c >> 2, j = c & 3;
-          const int v = vt * 128 + r;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {                           // 128 rows x 4 chunks of 16 B (32 fp16 of K)
+          const int c = it * 128 + lt, r = c >> 2, j = c & 3;
+          const int v = wi.vt * 128 + r;
           const bool ok = v < V;
           const size_t e = (size_t)(ok ? v : 0) * 32 + j * 8;
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
@@ -104,33 +139,27 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(w_bar) : "memory");
       }
       const uint32_t b_hi = smem_base + OFF_B + s * 2 * B_TILE, b_lo = b_hi + B_TILE;
-      const int p0 = pb * LP;
-      for (int c = lane; c < LP * 12 * 4; c += 32) {               // 16 poses x 12 entries x 4 chunks of 16 B
-        const int g = c >> 2, j = c & 3;                           // g = pose * 12 + entry: row g of the contiguous global block
-        const int p = g / 12, i = g - p * 12;
-        const bool ok = p0 + p < N;
-        const size_t e = ((size_t)(ok ? p0 : 0) * 12 + (ok ? g : 0)) * 32 + j * 8;
-        const int r = p * 16 + i;                                  // smem row: 16 per pose
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-        cp_async16(b_hi + off, a_hi + e, ok ? 16u : 0u);
-        cp_async16(b_lo + off, a_lo + e, ok ? 16u : 0u);
+      const int p0 = wi.pb() * LP;
+      const __half *gh = a_hi + (size_t)p0 * 12 * 32, *gl = a_lo + (size_t)p0 * 12 * 32;
+#pragma unroll
+      for (int it = 0; it < 6; ++it) {
+        const bool ok = p0 + (int)b_pose[it] < N;
+        cp_async16(b_hi + b_soff[it], ok ? gh + b_goff[it] : a_hi, ok ? 16u : 0u);
+        cp_async16(b_lo + b_soff[it], ok ? gl + b_goff[it] : a_lo, ok ? 16u : 0u);
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
     }
     cp_async_commit();
     cp_async_wait<0>();
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      int cur_vt = -1;
       uint32_t w_phase = 0;
-      for (int q = 0; q < my; ++q) {
-        const long long w = w0 + q;
-        const int vt = (int)(w / n_batches);
+      int q = 0;
+      for (WorkIter wi(N, V, blockIdx.x); wi.valid(); wi.next(gridDim.x), ++q) {
         const int s = q & 1;
         const uint32_t u = (uint32_t)(q >> 1);
-        if (vt != cur_vt) {
-          cur_vt = vt;
+        if (wi.first_of_run()) {
           mbar_wait(w_bar, w_phase);
           w_phase ^= 1u;
         }
@@ -160,10 +189,9 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
     const int half = tid >> 7;                                      // poses half*8 .. half*8+7 of the batch
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int vgrp = tid / 96, vj = tid - vgrp * 96;                // v_posed staging: threads 0..191 = 2 groups x 96 chunks of a pose row
-    auto issue_vp = [&](int q) {                                    // v_posed rows of batch q -> staging buffer q & 1
-      if (q < my && vgrp < 2) {
-        const long long w = w0 + q;
-        const int vt = (int)(w / n_batches), pb = (int)(w % n_batches);
+    auto issue_vp = [&](const WorkIter &wi, int q) {                // v_posed rows of this item -> staging buffer q & 1
+      if (wi.valid() && vgrp < 2) {
+        const int vt = wi.vt, pb = wi.pb();
         const uint32_t dst = smem_base + OFF_VP + (q & 1) * VP_STAGE;
         const int nv = (V - vt * 128) < 128 ? (V - vt * 128) : 128;
         const int chunks = (nv * 3 + 3) / 4;                        // 16-byte chunks per pose row (<= 96; reads stay inside the padded row)
@@ -178,14 +206,17 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
       }
       cp_async_commit();                                            // one (possibly empty) group per call keeps the wait counts uniform
     };
-    issue_vp(0);
-    issue_vp(1);
-    for (int q = 0; q < my; ++q) {
-      const long long w = w0 + q;
-      const int vt = (int)(w / n_batches), pb = (int)(w % n_batches);
+    WorkIter pre(N, V, blockIdx.x);                                 // prefetch cursor: two items ahead of the compute cursor
+    issue_vp(pre, 0);
+    if (pre.valid()) pre.next(gridDim.x);
+    issue_vp(pre, 1);
+    if (pre.valid()) pre.next(gridDim.x);
+    int q = 0;
+    for (WorkIter wi(N, V, blockIdx.x); wi.valid(); wi.next(gridDim.x), ++q) {
+      const int vt = wi.vt, pb = wi.pb();
       const int s = q & 1;
       const uint32_t u = (uint32_t)(q >> 1);
-      cp_async_wait<1>();                                           // this thread's copies of batch q have landed (batch q+1 may be in flight)
+      cp_async_wait<1>();                                           // this thread's copies of item q have landed (item q+1 may be in flight)
       named_bar_sync(1, 256);                                       // ... and everybody else's
       mbar_wait(tfull_bar(s), u & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -226,13 +257,14 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
         }
       }
       named_bar_sync(1, 256);                                       // staging buffer s is free again
-      issue_vp(q + 2);
+      issue_vp(pre, q + 2);
+      if (pre.valid()) pre.next(gridDim.x);
     }
     cp_async_wait<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
@@ -259,9 +291,9 @@ extern "C" int hd_smpl_lbs_tc(const void *w_hi, const void *w_lo, const void *a1
     if (num_sms[dev] <= 0) num_sms[dev] = 148;
     configured[dev] = true;
   }
-  const long long total = (long long)((V + 127) / 128) * ((N + hd::LP - 1) / hd::LP);
-  const int grid = (int)(total < num_sms[dev] ? total : num_sms[dev]);
-  hd::smpl_lbs_tc_kernel<<<grid, 320, hd::LBS_SMEM, (cudaStream_t)stream>>>(
+  const long long runs = (long long)((V + 127) / 128) * (((N + hd::LP - 1) / hd::LP + hd::RUN - 1) / hd::RUN);
+  const int grid = (int)(runs < num_sms[dev] ? runs : num_sms[dev]);
+  hd::smpl_lbs_tc_kernel<<<grid, 416, hd::LBS_SMEM, (cudaStream_t)stream>>>(
       reinterpret_cast<const __half *>(w_hi), reinterpret_cast<const __half *>(w_lo), reinterpret_cast<const __half *>(a12t_hi),
       reinterpret_cast<const __half *>(a12t_lo), v_posed, vp_ld, verts, N, V, out_mul, out_off);
   return hd::check_launch("smpl_lbs_tc_kernel");
