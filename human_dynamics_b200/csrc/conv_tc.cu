@@ -27,6 +27,7 @@
 //   WG3 warp 12 TMEM allocator + TMA producer for B, warp 13 MMA issuer    40 regs
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -849,15 +850,19 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       set_last_error_text("hd_conv_gemm(tc split-A): needs Cin % 64 == 0, in_ld % 8 == 0, aligned in_hi/in_lo, no prologue");
       return HD_ERR_INVALID;
     }
-    if (p.K <= 256) {    // HBM-shaped layers: one drain group per tile (<= 16 MMAs per accumulator)
+    {
+      // TMA epilogue (8 drain warps, staging ring, store / residual agents): every layer whose activation tensor maps were
+      // supplied.  Its main loop runs on 2 operand stages and drains the hi*hi accumulator every 4 chunks (16 truncating
+      // accumulations, ~4e-7 relative).  HD_TEPI_MAXK (env) restricts it to K <= that value (A/B switch; 256 = round-2 first cut).
+      static const int tepi_maxk = [] { const char *e = getenv("HD_TEPI_MAXK"); return e ? atoi(e) : (1 << 30); }();
       const bool res_plain = !p.res || (p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo);
       const bool maps = (!p.res || d->tmap_res) && (!p.out || d->tmap_out) && (!p.out_hi || (d->tmap_out_hi && d->tmap_out_lo));
-      if (maps && res_plain && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE))     // TMA epilogue
+      if (maps && res_plain && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE) && (p.K <= 256 || p.K <= tepi_maxk))
         return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, false, true>(p, d, st)
                             : launch_tc<128, true, 4, true, false, true, false, true>(p, d, st);
-      // strided-subsample residuals / no tensor maps: two drain/epilogue warp groups with per-thread global accesses
-      return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);
     }
+    if (p.K <= 256)      // (strided-subsample residuals / no tensor maps) two drain/epilogue warp groups with per-thread global accesses
+      return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);
     return p.Cout <= 64 ? launch_tc<64, true, 2, true, false, true>(p, d, st) : launch_tc<128, true, 2, true, false, true>(p, d, st);
   }
   if (half && p.Cin % bke != 0) {      // ragged Cin (resnet conv1: 7x7x3): element-wise gather producer, K zero-padded

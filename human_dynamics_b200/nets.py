@@ -213,11 +213,11 @@ class ConvOp(object):
 
     def encode_act_maps(self):
         """(Re-)encode the activation tensor maps of the TMA epilogue for the pointers currently in the descriptor.
-        Only layers the kernel can run that way get maps (conv_tc.cu launch_conv_tc): fp16-split input, K <= 256,
-        Cout % 32 == 0, residual row == output row; everything else keeps the per-thread epilogue."""
+        Only layers the kernel can run that way get maps (conv_tc.cu launch_conv_tc): fp16-split input, Cout % 32 == 0,
+        residual row == output row; everything else keeps the per-thread epilogue."""
         d = self.d
         K = d.KH * d.KW * d.Cin
-        ok = (d.impl == _lib.HD_IMPL_TC_3XF16 and d.in_hi and K <= 256 and d.Cout % 32 == 0 and
+        ok = (d.impl == _lib.HD_IMPL_TC_3XF16 and d.in_hi and d.Cout % 32 == 0 and
               (not d.res or (d.res_stride == 1 and d.res_H == d.Ho and d.res_W == d.Wo)))
         for f in ('tmap_res', 'tmap_out', 'tmap_out_hi', 'tmap_out_lo'):
             setattr(d, f, None)
