@@ -103,9 +103,15 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::BAR_OFFSET + 8 * (2 * STAGES + 6));
   // TEPI staging ring (the gap up to EPI_OFFSET holds these): residual slab landed in buffer b / slab b computed and written by the
   // 128 drain threads / the TMA stores of buffer b have read it
-  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };
-  auto ready_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 10 + b); };
-  auto free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 13 + b); };
+  // The two drain groups use a buffer alternately (its uses u = 0, 1, 2, ... belong to groups g, 1-g, g, ...).  A parity wait is only
+  // safe for a waiter that observes every phase of its barrier, so "residual landed" and "buffer free" exist twice per buffer, one
+  // barrier per use parity: each is then waited on by ONE group (or by the in-order residual agent) in consecutive phases.
+  auto res_bar = [&](int b, int u) { return bar_base + 8u * (2 * STAGES + 7 + b * 2 + (u & 1)); };          // phase u >> 1
+  auto ready_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 13 + b); };                            // phase u (store agent, in order)
+  auto free_bar = [&](int b, int u) { return bar_base + 8u * (2 * STAGES + 16 + b * 2 + (u & 1)); };        // enables use u >= 1
+  auto wait_free = [&](int b, int u) {          // the stores of use u-1 of buffer b have read it
+    if (u > 0) mbar_wait(free_bar(b, u), (uint32_t)((u & 1) ? (u >> 1) : (u >> 1) - 1) & 1u);
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (GATHER ? p.K_pad : p.K) / BKE;   // GATHER: ragged Cin (conv1: K=147 zero-padded to 192)
@@ -127,9 +133,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     if (TEPI)
       for (int b = 0; b < C::EPI_NB; ++b) {
-        mbar_init(res_bar(b), 1);
+        mbar_init(res_bar(b, 0), 1);
+        mbar_init(res_bar(b, 1), 1);
         mbar_init(ready_bar(b), 128);
-        mbar_init(free_bar(b), 1);
+        mbar_init(free_bar(b, 0), 1);
+        mbar_init(free_bar(b, 1), 1);
       }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -564,8 +572,9 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           const int gi = ti * NSL + sl;                 // running slab index of this CTA (the agents walk them in this order)
           const int b = gi % NB;
           uint8_t *buf = smem + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
-          if (has_res) mbar_wait(res_bar(b), (uint32_t)(gi / NB) & 1u);              // residual landed (=> buffer was free)
-          else mbar_wait(free_bar(b), ((uint32_t)(gi / NB) & 1u) ^ 1u);             // stores of slab gi - NB have read the buffer
+          const int use = gi / NB;
+          if (has_res) mbar_wait(res_bar(b, use), (uint32_t)(use >> 1) & 1u);        // residual landed (=> buffer was free)
+          else wait_free(b, use);                                                    // stores of slab gi - NB have read the buffer
           uint8_t *frow = buf + row * 128;
           uint8_t *hrow = buf + C::EPI_F32_BYTES + row * 64;
           uint8_t *lrow = hrow + C::EPI_H_BYTES;
@@ -672,9 +681,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             const int tilen = tile + (int)gridDim.x;
             tma_prefetch_2d(&em.res, (tilen % tiles_n) * BN + sl * 32, (tilen / tiles_n) * BM);
           }
-          mbar_wait(free_bar(b), ((uint32_t)(j / NB) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(res_bar(b), C::EPI_F32_BYTES);
-          tma_load_2d(smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES, &em.res, res_bar(b), c0, c1);
+          const int use = j / NB;
+          wait_free(b, use);
+          mbar_arrive_expect_tx(res_bar(b, use), C::EPI_F32_BYTES);
+          tma_load_2d(smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES, &em.res, res_bar(b, use), c0, c1);
         }
       }
     } else if (TEPI && warp == W_ST) {
@@ -698,7 +708,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           }
           bulk_commit();
           bulk_wait_read<0>();                     // only this agent waits for the TMA engine; then the buffer goes back into the ring
-          mbar_arrive(free_bar(b));
+          mbar_arrive(free_bar(b, j / NB + 1));    // enables the buffer's next use
         }
       }
     } else if (warp == W_MMA) {
