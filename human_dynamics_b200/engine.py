@@ -58,6 +58,21 @@ def load_mean_params(path):
     return np.hstack(([0.9, 0.0, 0.0], pose, shape.reshape(10))).astype(np.float32).reshape(1, 85)
 
 
+class _Bounded(dict):
+    """dict that forgets its oldest entries beyond `maxlen` (plan / buffer caches keyed by batch shape: a service that sees
+    many different shapes must not grow device memory without bound; evicted plans are simply rebuilt on next use)."""
+
+    def __init__(self, maxlen):
+        super().__init__()
+        self.maxlen = maxlen
+
+    def __setitem__(self, key, value):
+        if key not in self:
+            while len(self) >= self.maxlen:
+                self.pop(next(iter(self)))
+        super().__setitem__(key, value)
+
+
 class PackedHal(object):
     """fc2_res hallucinator (models.py:270-296)."""
 
@@ -84,13 +99,13 @@ class HMMREngine(object):
             self.ief = PackedIEF(w, self.device, delta_t_values=self.delta_t_values, tc=tc)
             self.hal = PackedHal(w, self.device, tc=tc) if 'fc2_res/fc1/weights' in w else None
             self.smpl = smpl_model if isinstance(smpl_model, SMPLConstants) else SMPLConstants(smpl_model, device=self.device)
-        self._resnet_plans = {}
-        self._fmovie_plans = {}
-        self._ief_plans = {}
-        self._hal_plans = {}
-        self._theta0 = {}
-        self._phi = {}
-        self._outs = {}
+        self._resnet_plans = _Bounded(8)
+        self._fmovie_plans = _Bounded(4)
+        self._ief_plans = _Bounded(4)
+        self._hal_plans = _Bounded(4)
+        self._theta0 = _Bounded(8)
+        self._phi = _Bounded(96)
+        self._outs = _Bounded(4)
         self._graphs = {}
 
     # ---------------------------------------------------------------- stage API
@@ -285,7 +300,10 @@ class HMMREngine(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self.predict(images, single_frame=single_frame)
-            ent = (g, out, int(_lib.lib.hd_launch_count()) - n0, images)
+            # the graph holds raw device pointers: pin everything the caches held at capture time so a later eviction cannot free it
+            keep = [dict(c) for c in (self._resnet_plans, self._fmovie_plans, self._ief_plans, self._hal_plans, self._theta0,
+                                      self._phi, self._outs)] + [dict(self.smpl._tc_bufs)]
+            ent = (g, out, int(_lib.lib.hd_launch_count()) - n0, images, keep)
             self._graphs[key] = ent
         ent[0].replay()
         return ent[1], ent[2]
