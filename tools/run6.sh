@@ -8,5 +8,5 @@ run 600 memcheck_smpl  $S --tool memcheck --print-limit 5 python -m pytest tests
 run 300 memcheck_prep  $S --tool memcheck --print-limit 5 python -m pytest tests/test_preprocess.py -q -m gpu -x -k "run_video"
 run 600 racecheck_conv $S --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_nets.py -q -m gpu -x -k "presplit and True-shape0"
 run 600 synccheck_conv $S --tool synccheck --print-limit 5 python -m pytest tests/test_gpu_nets.py -q -m gpu -x -k "presplit and True-shape0"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 230 -c 260 --csv --log-file gpurun_out/r6_launches_step.csv python tools/prof_step.py 2 > gpurun_out/r6_launches.log 2>&1; tail -2 gpurun_out/r6_launches.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 199 -c 199 --csv --log-file gpurun_out/r6_launches_step.csv python tools/prof_step.py 2 > gpurun_out/r6_launches.log 2>&1; tail -2 gpurun_out/r6_launches.log
 for fc in 128 320; do HD_FRAME_CHUNK=$fc timeout 300 python bench.py --steps 5 --no-cpu-baseline --no-extra > gpurun_out/r6_bench_fc$fc.json 2>/dev/null; head -c 220 gpurun_out/r6_bench_fc$fc.json; echo; done
