@@ -9,7 +9,7 @@
 // remainder needs no scaling and all three products share one accumulator).  Each epilogue thread owns one vertex: per pose
 // it reads the 12 entries of T from TMEM, applies them to v_posed (staged by cp.async as 1536-byte row segments) and leaves
 // the result in the same staging slot; the CTA then writes 16 x 1536 contiguous bytes with 8-byte vector stores.
-// HBM traffic = read v_posed + write verts; W tile and the A12 operand blocks (75 MB for 65536 poses) live in smem / L2.
+// HBM traffic = read v_posed + write verts (+ the A12 operand once: 100 MB for 65536 poses); the weight tiles live in L2.
 //
 // Warp roles (416 threads): warps 0-7 epilogue (thread = vertex row; warps 0-3 take poses 0-7 of a batch, warps 4-7 poses 8-15,
 // two warps per scheduler hide each other's TMEM / shared-memory latency), warps 8-11 operand loaders (cp.async into
@@ -27,43 +27,31 @@ constexpr int W_TILE = 128 * 128;               // 128 vertex rows x 128-byte sw
 constexpr int B_TILE = LN * 128;                // 256 rows (rows 12..15 of every pose are never written or read back)
 constexpr int VP_ROW = 128 * 3 * 4;             // 1536 B: 128 vertices x xyz fp32
 constexpr int VP_STAGE = LP * VP_ROW;           // 24 KiB
-constexpr int OFF_W = 0;                        // W hi, W lo
-constexpr int OFF_B = OFF_W + 2 * W_TILE;       // 2 stages x (hi, lo)
-constexpr int OFF_VP = OFF_B + 2 * 2 * B_TILE;  // 2 stages
+constexpr int OFF_W = 0;                        // 2 stages x (hi, lo): the vertex tile's weights change every item
+constexpr int OFF_B = OFF_W + 2 * 2 * W_TILE;   // (hi, lo): the pose batch's transforms stay for all 54 vertex tiles
+constexpr int OFF_VP = OFF_B + 2 * B_TILE;      // 2 stages
 constexpr int OFF_BAR = OFF_VP + 2 * VP_STAGE;
 constexpr int LBS_SMEM = OFF_BAR + 128 + 1024;
 constexpr uint32_t LBS_IDESC = (1u << 4) | ((uint32_t)(LN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // f16 x f16 -> f32, M=128, N=256
 constexpr int TMEM_COLS = 512;                  // 2 accumulators of 256 columns
 
-constexpr int RUN = 64;                         // consecutive pose batches of one vertex tile handled by one CTA before it moves on
-
-// Work order.  Items are (vertex tile, pose batch); they are grouped into runs of RUN consecutive batches of one vertex tile, the
-// runs are ordered pose-block-major ([pose block][vertex tile]) and dealt round-robin to the CTAs.  All CTAs therefore sweep the
-// pose dimension together: at any moment the chip touches a window of ~3 * RUN * 16 poses of the A12 operand (a few MB, L2-hot,
-// read by all 54 vertex tiles) while v_posed / verts stream through once; the W tile is reloaded once per run.
+// Work order.  An item is (pose batch, vertex tile); a run is one pose batch with all its vertex tiles, runs are dealt round-robin
+// to the CTAs.  A CTA therefore reads / writes whole 82 KB pose rows front to back in 1536-byte steps (DRAM-page and TLB friendly;
+// walking the pose dimension for a fixed vertex tile instead touched a new page every access), keeps the batch's A12 operand in
+// shared memory for the whole run, and streams the 54 weight tiles (442 KB in all, L2-resident) through a 2-stage ring.
 struct WorkIter {
-  int n_batches, n_vt, total_runs, run, k, nb, vt, pb0;
+  int n_batches, n_vt, run, vt;
   __device__ WorkIter(int N, int V, int first_run) {
     n_batches = (N + LP - 1) / LP;
     n_vt = (V + 127) / 128;
-    total_runs = ((n_batches + RUN - 1) / RUN) * n_vt;
     run = first_run;
-    k = 0;
-    load();
+    vt = 0;
   }
-  __device__ void load() {
-    if (run < total_runs) {
-      const int sb = run / n_vt;
-      vt = run - sb * n_vt;
-      pb0 = sb * RUN;
-      nb = (n_batches - pb0) < RUN ? (n_batches - pb0) : RUN;
-    }
-  }
-  __device__ bool valid() const { return run < total_runs; }
-  __device__ int pb() const { return pb0 + k; }
-  __device__ bool first_of_run() const { return k == 0; }
+  __device__ bool valid() const { return run < n_batches; }
+  __device__ int pb() const { return run; }
+  __device__ bool first_of_run() const { return vt == 0; }
   __device__ void next(int stride) {
-    if (++k == nb) { k = 0; run += stride; load(); }
+    if (++vt == n_vt) { vt = 0; run += stride; }
   }
 };
 
@@ -76,11 +64,11 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar = smem_base + OFF_BAR;
-  auto full_bar = [&](int s) { return bar + 8u * s; };            // B operands of stage s landed (128 loader lanes)
-  auto empty_bar = [&](int s) { return bar + 8u * (2 + s); };     // MMAs that read stage s (and the W tile) completed
+  auto full_bar = [&](int s) { return bar + 8u * s; };            // weight tile of stage s landed (128 loader lanes)
+  auto empty_bar = [&](int s) { return bar + 8u * (2 + s); };     // MMAs that read stage s (and the A12 tile) completed
   auto tfull_bar = [&](int s) { return bar + 8u * (4 + s); };     // accumulator s complete
   auto tempty_bar = [&](int s) { return bar + 8u * (6 + s); };    // accumulator s drained (8 epilogue warps)
-  const uint32_t w_bar = bar + 8u * 8;                            // W tile landed
+  const uint32_t w_bar = bar + 8u * 8;                            // A12 tile of the run landed
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 8 * 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +96,7 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
   if (warp >= W_LOAD && warp < W_MMA) {
     // =============================== operand loaders (128 lanes) ===============================
     const int lt = threadIdx.x - W_LOAD * 32;
-    // this lane's 6 chunk pairs of a B block (16 poses x 12 entries x 4 chunks of 16 B) and 4 of the W tile: constant per lane
+    // this lane's 6 chunk pairs of an A12 block (16 poses x 12 entries x 4 chunks of 16 B): constant per lane
     uint32_t b_soff[6], b_goff[6], b_pose[6];
 #pragma unroll
     for (int it = 0; it < 6; ++it) {
@@ -122,30 +110,30 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
     for (WorkIter wi(N, V, blockIdx.x); wi.valid(); wi.next(gridDim.x), ++q) {
       const int s = q & 1;
       const uint32_t u = (uint32_t)(q >> 1);
-      mbar_wait(empty_bar(s), (u & 1u) ^ 1u);                       // MMAs of batch q-2 have read stage s
+      mbar_wait(empty_bar(s), (u & 1u) ^ 1u);                       // MMAs of item q-2 have read weight stage s
       if (wi.first_of_run()) {
-        // new vertex tile: every earlier MMA (they read the W tile) must have completed before it is overwritten
+        // new pose batch: every earlier MMA (they read the A12 tile) must have completed before it is overwritten
         if (q >= 1) mbar_wait(empty_bar((q - 1) & 1), ((uint32_t)((q - 1) >> 1)) & 1u);
+        const int p0 = wi.pb() * LP;
+        const __half *gh = a_hi + (size_t)p0 * 12 * 32, *gl = a_lo + (size_t)p0 * 12 * 32;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {                           // 128 rows x 4 chunks of 16 B (32 fp16 of K)
-          const int c = it * 128 + lt, r = c >> 2, j = c & 3;
-          const int v = wi.vt * 128 + r;
-          const bool ok = v < V;
-          const size_t e = (size_t)(ok ? v : 0) * 32 + j * 8;
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          cp_async16(smem_base + OFF_W + off, w_hi + e, ok ? 16u : 0u);
-          cp_async16(smem_base + OFF_W + W_TILE + off, w_lo + e, ok ? 16u : 0u);
+        for (int it = 0; it < 6; ++it) {
+          const bool ok = p0 + (int)b_pose[it] < N;
+          cp_async16(smem_base + OFF_B + b_soff[it], ok ? gh + b_goff[it] : a_hi, ok ? 16u : 0u);
+          cp_async16(smem_base + OFF_B + B_TILE + b_soff[it], ok ? gl + b_goff[it] : a_lo, ok ? 16u : 0u);
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(w_bar) : "memory");
       }
-      const uint32_t b_hi = smem_base + OFF_B + s * 2 * B_TILE, b_lo = b_hi + B_TILE;
-      const int p0 = wi.pb() * LP;
-      const __half *gh = a_hi + (size_t)p0 * 12 * 32, *gl = a_lo + (size_t)p0 * 12 * 32;
+      const uint32_t w_s = smem_base + OFF_W + s * 2 * W_TILE;
 #pragma unroll
-      for (int it = 0; it < 6; ++it) {
-        const bool ok = p0 + (int)b_pose[it] < N;
-        cp_async16(b_hi + b_soff[it], ok ? gh + b_goff[it] : a_hi, ok ? 16u : 0u);
-        cp_async16(b_lo + b_soff[it], ok ? gl + b_goff[it] : a_lo, ok ? 16u : 0u);
+      for (int it = 0; it < 4; ++it) {                             // 128 rows x 4 chunks of 16 B (32 fp16 of K)
+        const int c = it * 128 + lt, r = c >> 2, j = c & 3;
+        const int v = wi.vt * 128 + r;
+        const bool ok = v < V;
+        const size_t e = (size_t)(ok ? v : 0) * 32 + j * 8;
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+        cp_async16(w_s + off, w_hi + e, ok ? 16u : 0u);
+        cp_async16(w_s + W_TILE + off, w_lo + e, ok ? 16u : 0u);
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
     }
@@ -168,9 +156,9 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // cp.async (generic proxy) data -> UMMA (async proxy)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem + (uint32_t)(s * 256);
-        const uint64_t da_hi = make_smem_desc(smem_base + OFF_W), da_lo = make_smem_desc(smem_base + OFF_W + W_TILE);
-        const uint32_t b_hi = smem_base + OFF_B + s * 2 * B_TILE;
-        const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_hi + B_TILE);
+        const uint32_t w_s = smem_base + OFF_W + s * 2 * W_TILE;
+        const uint64_t da_hi = make_smem_desc(w_s), da_lo = make_smem_desc(w_s + W_TILE);
+        const uint64_t db_hi = make_smem_desc(smem_base + OFF_B), db_lo = make_smem_desc(smem_base + OFF_B + B_TILE);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {                               // K = 32 fp16 = two UMMA K steps of 32 bytes
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -291,7 +279,7 @@ extern "C" int hd_smpl_lbs_tc(const void *w_hi, const void *w_lo, const void *a1
     if (num_sms[dev] <= 0) num_sms[dev] = 148;
     configured[dev] = true;
   }
-  const long long runs = (long long)((V + 127) / 128) * (((N + hd::LP - 1) / hd::LP + hd::RUN - 1) / hd::RUN);
+  const long long runs = (N + hd::LP - 1) / hd::LP;                 // one run = one batch of 16 poses over all vertex tiles
   const int grid = (int)(runs < num_sms[dev] ? runs : num_sms[dev]);
   hd::smpl_lbs_tc_kernel<<<grid, 416, hd::LBS_SMEM, (cudaStream_t)stream>>>(
       reinterpret_cast<const __half *>(w_hi), reinterpret_cast<const __half *>(w_lo), reinterpret_cast<const __half *>(a12t_hi),
