@@ -368,6 +368,12 @@ def main():
     if args.workload != 'smpl':
         sel_idx = [0, B - 1]
         timed_out = {k: last['out'][k][sel_idx].float().cpu().numpy() for k in PARITY_KEYS if k in last['out']}
+    gather_ok = None
+    if world > 1 and rank == 0 and last.get('g') is not None:
+        # gathered tensors must contain rank 0's own clips bit for bit (the N-GPU == 1-GPU identity is tests/test_multi_gpu.py);
+        # checked here, before the end-to-end legs reuse the output buffers
+        torch.cuda.synchronize()
+        gather_ok = bool(all(torch.equal(last['g'][k][:B], last['out'][k]) for k in gather_keys))
     graph_nodes = None
     if args.workload != 'smpl' and args.graph and last.get('nodes'):
         graph_nodes = int(last['nodes'])
@@ -449,10 +455,8 @@ def main():
                       'checked': 'last timed step, %s {0, %d} of %d vs the float32 oracle port' % ('frames' if single else 'clips', B - 1, B)}
             sample += ' = %s {0, %d} of the timed input' % ('frames' if single else 'clips', B - 1)
         cpu_baseline = {'value': v, 'unit': unit_name, 'cores': cores, 'kind': 'port', 'sample': sample}
-    if rank == 0 and world > 1 and last.get('g') is not None:
-        # gathered tensors must contain rank 0's own clips bit for bit (the N-GPU == 1-GPU identity is tests/test_multi_gpu.py)
-        ok = all(torch.equal(last['g'][k][:B], last['out'][k]) for k in gather_keys)
-        parity = {'gather_own_shard_bit_identical': bool(ok)}
+    if gather_ok is not None:
+        parity = {'gather_own_shard_bit_identical': gather_ok}
 
     # ------------------------------------------------------------------ the other single-GPU BASELINE configs, device-resident
     extra = None
