@@ -209,8 +209,13 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           const bool ok = tap_ok && rs.n[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
           const size_t e = ok ? ((size_t)((size_t)rs.n[i] * p.H + iy) * p.W + ix) * p.in_ld + ci : 0;
           const uint32_t off = (uint32_t)(rb + 32 * i) * 128u + sw_off;
-          cp_async16(a_hi + off, ihi + e, ok ? 16u : 0u);
-          cp_async16(a_lo + off, ilo + e, ok ? 16u : 0u);
+          if (p.planes) {        // conv1: neighbouring output pixels read overlapping 64-byte windows (each 16-byte piece 4x): keep them in L1
+            cp_async16_ca(a_hi + off, ihi + e, ok ? 16u : 0u);
+            cp_async16_ca(a_lo + off, ilo + e, ok ? 16u : 0u);
+          } else {
+            cp_async16(a_hi + off, ihi + e, ok ? 16u : 0u);
+            cp_async16(a_lo + off, ilo + e, ok ? 16u : 0u);
+          }
         }
         // the barrier itself is told to arrive (without a pending-count increment) once this thread's copies have landed:
         // chunks are published the moment their data is in smem, with no producer thread in the loop, so up to STAGES
