@@ -607,13 +607,16 @@ def measure_roofline(args, peaks, env):
     peak = peaks['bf16_tflops_sustained']
     step_s = env['ms'] * 1e-3
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.exists(tpath) and args.mode in ('auto', 'tc3h'):
         with open(tpath) as f:
             tj = json.load(f)
-        traffic = {'dram_bytes_per_launch': tj['tensor_bound_launch']['dram_bytes'],
-                   'algorithmic_bytes_per_launch': tj['tensor_bound_launch']['algorithmic_bytes'],
-                   'launch': tj['tensor_bound_launch']['layer'], 'source': 'profiles/r01_traffic.json (one ncu --set full capture)'}
+        tb, mb = tj['tensor_bound_launch'], tj['memory_bound_launch']
+        traffic = {'dram_bytes_per_launch': tb['dram_bytes'], 'algorithmic_bytes_per_launch': tb['algorithmic_bytes'], 'launch': tb['layer'],
+                   'memory_bound_launch': {'dram_bytes_per_launch': mb['dram_bytes'], 'algorithmic_bytes_per_launch': mb['algorithmic_bytes'],
+                                           'launch': mb['layer']},
+                   'source': 'profiles/r02_traffic.json: ncu --set full captures of this round\'s kernels (tools/make_traffic_json.py); '
+                             'bench.py cannot run ncu on itself, so the file is regenerated whenever the kernel changes'}
     return {'bound': 'tensor', 'kernel': kind, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
             'launches_per_step': n_tc, 'avg_launch_us': tc_time / n_tc * 1e6, 'algorithmic_flops_per_launch_avg': tc_flops / n_tc,
             'share_of_step': tc_time / step_s,
