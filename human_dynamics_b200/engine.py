@@ -7,6 +7,7 @@ streams and host<->device copies only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -56,6 +57,26 @@ def load_mean_params(path):
     pose[:3] = 0.0
     pose[0] = np.pi                                                            # tester.py:126-127
     return np.hstack(([0.9, 0.0, 0.0], pose, shape.reshape(10))).astype(np.float32).reshape(1, 85)
+
+
+NVTX = os.environ.get('HD_NVTX', '0') != '0'      # NVTX ranges per stage (for nsys / ncu --nvtx timelines); off by default
+
+
+class _nvtx(object):
+    """`with _nvtx('stage'):` -- a torch.cuda.nvtx range when HD_NVTX=1, nothing otherwise."""
+    __slots__ = ('name',)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class _Bounded(dict):
@@ -173,7 +194,8 @@ class HMMREngine(object):
                     main.wait_event(ev)
             plan.set_output(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
             if frames is None:
-                plan.run(images[i:i + n], None, st)
+                with _nvtx('resnet root + blocks 1-2 [%d:%d]' % (i, i + n)):
+                    plan.run(images[i:i + n], None, st)
             else:
                 fr, geom = frames
                 H, W = fr.shape[1], fr.shape[2]
@@ -194,7 +216,8 @@ class HMMREngine(object):
             n = min(cB, N - i)
             plan = self._resnet_plan(n, size, 'B')
             plan.set_input(mid[i:i + n], (mid_split[0][i:i + n], mid_split[1][i:i + n]) if mid_split else None)
-            plan.run(None, phi[i:i + n], st)
+            with _nvtx('resnet blocks 3-4 + pool5 [%d:%d]' % (i, i + n)):
+                plan.run(None, phi[i:i + n], st)
         return phi
 
     def encode_images(self, images, out=None):
@@ -403,13 +426,15 @@ class HMMREngine(object):
         else:
             mode = self.config.pred_mode
             if mode == 'pred':
-                strips = self.temporal_encode(phi)
+                with _nvtx('f_movie'):
+                    strips = self.temporal_encode(phi)
             elif mode == 'hal':
                 strips = self.hallucinate(phi)
             else:
                 raise Exception('Pred mode {} not recognized'.format(mode))
             plan = self._ief_plan(N, tuple(sorted(self.ief.deltas.keys())))
-            omega = plan.run_main(strips.reshape(N, -1), self.theta_mean(N))
+            with _nvtx('IEF main head'):
+                omega = plan.run_main(strips.reshape(N, -1), self.theta_mean(N))
             deltas = None
         dts = sorted(self.ief.deltas.keys()) if not single_frame else []
         D = len(dts)
@@ -417,20 +442,23 @@ class HMMREngine(object):
         o0, od = self._out_buffers(N, D)
         cams = omega[:, 0:3]
         # OmegasPred.compute_smpl (omega.py:263-304) for the dt=0 instance ...
-        self.smpl.forward(omega[:, 75:85], omega[:, 3:75], cam=cams, out=o0)
+        with _nvtx('SMPL dt=0'):
+            self.smpl.forward(omega[:, 75:85], omega[:, 3:75], cam=cams, out=o0)
         out = {'cams': cams.reshape(B, T, 3), 'joints': o0['joints'].view(B, T, K, 3), 'kps': o0['kps'].view(B, T, K, 2),
                'poses': o0['Rs'].view(B, T, 24, 3, 3), 'shapes': omega[:, 75:85].reshape(B, T, 10),
                'verts': o0['verts'].view(B, T, V, 3), 'omegas': omega.view(B, T, 85)}
         if on_main_ready is not None:        # the dt=0 results can start their trip to the host while the delta heads compute
             on_main_ready(out)
         if D:
-            deltas = self._ief_plan(N, tuple(dts)).run_deltas()
+            with _nvtx('IEF delta heads'):
+                deltas = self._ief_plan(N, tuple(dts)).run_deltas()
         if D:
             # ... and every delta instance; cams come from the dt=0 prediction (set_cams, tester.py:210-213).
             # Pose n of delta i is written to slot n*D+i, i.e. directly into the [B,T,D,...] stacking of tester.py:252.
             for i, dt in enumerate(dts):
                 d = deltas[dt]
-                self.smpl.forward(d[:, 75:85], d[:, 3:75], cam=cams, out=od, slot=(D, i))
+                with _nvtx('SMPL dt=%+d' % dt):
+                    self.smpl.forward(d[:, 75:85], d[:, 3:75], cam=cams, out=od, slot=(D, i))
             omegas_delta = self._ief_plan(N, tuple(dts)).delta_all.view(B, T, D, 85)
             out.update({'cams_delta': cams.reshape(B, T, 1, 3).expand(B, T, D, 3),
                         'joints_delta': od['joints'].view(B, T, D, K, 3), 'kps_delta': od['kps'].view(B, T, D, K, 2),
