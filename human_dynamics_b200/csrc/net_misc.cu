@@ -167,6 +167,160 @@ __global__ void subsample_kernel(const float4 *__restrict__ in, float4 *__restri
   out[i] = __ldg(in + ((size_t)((size_t)n * H + (size_t)oy * s) * W + (size_t)ox * s) * C4 + c);
 }
 
+// GroupNorm + ReLU + fp16 split in one pass (f_movie pre-activations, src/models.py:155-171,188-204): one warp per (clip, group).
+// Same statistics and the same affine as groupnorm_stats_kernel + the conv prologue it replaces (y = relu(x*gain + offset), gain =
+// rstd*gamma, offset = beta - mean*gain; identical summation order), but the result leaves as the pre-split A operand of the
+// tensor-core conv, so the temporal convs take the cp.async producer instead of the register-staged one.  T*cg <= 40*32 elements.
+__global__ void __launch_bounds__(128) groupnorm_relu_split_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                                   const float *__restrict__ beta, __half *__restrict__ out_hi,
+                                                                   __half *__restrict__ out_lo, int B, int T, int C, int groups, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wg >= B * groups) return;
+  const int b = wg / groups, g = wg % groups;
+  const int cg = C / groups;
+  const size_t base = (size_t)b * T * C + (size_t)g * cg;
+  const int cnt = T * cg;
+  constexpr int MAXE = 40;
+  float v[MAXE];
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    v[e] = i < cnt ? __ldg(x + base + (size_t)(i / cg) * C + (i % cg)) : 0.f;
+    if (i < cnt) s += v[e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)cnt;
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    if (i < cnt) { const float d = v[e] - mean; q += d * d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)cnt + eps);
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    if (i >= cnt) continue;
+    const int ch = g * cg + (i % cg);
+    const float gn = rstd * __ldg(gamma + ch);
+    const float off = __ldg(beta + ch) - mean * gn;
+    const float y = fmaxf(v[e] * gn + off, 0.f);
+    uint32_t h, l;
+    hd::split_f16x2(y, 0.f, h, l);
+    const size_t o = base + (size_t)(i / cg) * C + (i % cg);
+    out_hi[o] = __ushort_as_half((unsigned short)(h & 0xffffu));
+    out_lo[o] = __ushort_as_half((unsigned short)(l & 0xffffu));
+  }
+}
+
+// fp32 -> fp16 head / remainder pair (the A operand format of the tensor-core GEMM), 4 elements per thread.
+__global__ void split_f16_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(x + i);
+  uint32_t h0, l0, h1, l1;
+  hd::split_f16x2(v.x, v.y, h0, l0);
+  hd::split_f16x2(v.z, v.w, h1, l1);
+  hi[i] = make_uint2(h0, h1);
+  lo[i] = make_uint2(l0, l1);
+}
+
+// IEF fc1, theta part (src/models.py:402,102: state = concat[phi, theta] -> fc1): h1 = relu(P + theta . W1[2048:]) with P = phi . W1[:2048]
+// + b1 hoisted out of the stage loop.  K = 85 / 72 is far too short for the tensor-core tile; here a block takes 8 rows and all C
+// columns (thread = 4 columns), theta rows sit in smem, W streams from L2 (348 KB, read once per block).  Output = the pre-split
+// fp16 pair fc2's cp.async producer loads (and optionally fp32).
+__global__ void __launch_bounds__(256) ief_fc1_theta_kernel(const float *__restrict__ P, const float *__restrict__ theta, int theta_ld,
+                                                            const float *__restrict__ W, int K, int Cc, __half *__restrict__ out_hi,
+                                                            __half *__restrict__ out_lo, float *__restrict__ out_f32, int N) {
+  __shared__ float th[8][96];
+  const int r0 = blockIdx.x * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    th[r][k] = (r0 + r < N) ? __ldg(theta + (size_t)(r0 + r) * theta_ld + k) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 4; c < Cc; c += 1024) {
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    for (int k = 0; k < K; ++k) {
+      const float4 w = __ldg(reinterpret_cast<const float4 *>(W + (size_t)k * Cc + c));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float t = th[r][k];
+        acc[r][0] += t * w.x; acc[r][1] += t * w.y; acc[r][2] += t * w.z; acc[r][3] += t * w.w;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r0 + r >= N) break;
+      const size_t o = (size_t)(r0 + r) * Cc + c;
+      const float4 p = __ldg(reinterpret_cast<const float4 *>(P + o));
+      const float y0 = fmaxf(acc[r][0] + p.x, 0.f), y1 = fmaxf(acc[r][1] + p.y, 0.f), y2 = fmaxf(acc[r][2] + p.z, 0.f),
+                  y3 = fmaxf(acc[r][3] + p.w, 0.f);
+      if (out_f32) *reinterpret_cast<float4 *>(out_f32 + o) = make_float4(y0, y1, y2, y3);
+      if (out_hi) {
+        uint32_t h0, l0, h1, l1;
+        hd::split_f16x2(y0, y1, h0, l0);
+        hd::split_f16x2(y2, y3, h1, l1);
+        *reinterpret_cast<uint2 *>(out_hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2 *>(out_lo + o) = make_uint2(l0, l1);
+      }
+    }
+  }
+}
+
+// IEF fc3 + update (models.py:113,410): theta_out = theta_prev + h2 . W3 + b3, W3 [K, D] with D = 85 / 72: one tensor-core tile
+// would serialise K = 1024 on 5 CTAs.  Block = 8 rows x 8 warps; warp w sums k in [w*K/8, (w+1)*K/8) for the block's rows (lane = output
+// column, 3 per lane), partial sums meet in smem in warp order: fixed summation order, bit-reproducible.
+__global__ void __launch_bounds__(256) ief_fc3_kernel(const float *__restrict__ h2, const float *__restrict__ W, const float *__restrict__ bias,
+                                                      const float *__restrict__ prev, int prev_ld, float *__restrict__ out, int out_ld, int N,
+                                                      int K, int D) {
+  extern __shared__ float sm[];
+  float *hs = sm;                         // [8][K]
+  float *part = sm + 8 * K;               // [8 warps][8 rows][96]
+  const int r0 = blockIdx.x * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    hs[i] = (r0 + r < N) ? __ldg(h2 + (size_t)(r0 + r) * K + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[8][3];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.f;
+  const int kper = K / 8;
+  const bool c1 = lane + 32 < D, c2 = lane + 64 < D;
+  for (int k = warp * kper; k < (warp + 1) * kper; ++k) {
+    const float *wr = W + (size_t)k * D;
+    const float w0 = __ldg(wr + lane), w1 = c1 ? __ldg(wr + lane + 32) : 0.f, w2 = c2 ? __ldg(wr + lane + 64) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float h = hs[r * K + k];
+      acc[r][0] += h * w0; acc[r][1] += h * w1; acc[r][2] += h * w2;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float *pp = part + (warp * 8 + r) * 96;
+    pp[lane] = acc[r][0]; pp[lane + 32] = acc[r][1]; pp[lane + 64] = acc[r][2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * D; i += 256) {
+    const int r = i / D, j = i - r * D;
+    if (r0 + r >= N) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[(w * 8 + r) * 96 + j];
+    out[(size_t)(r0 + r) * out_ld + j] = (s + __ldg(bias + j)) + prev[(size_t)(r0 + r) * prev_ld + j];
+  }
+}
+
 __global__ void ief_delta_init_kernel(const float *__restrict__ theta, float *__restrict__ dst, int dst_ld, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 85) return;
@@ -259,4 +413,49 @@ extern "C" int hd_subsample(const float *in, float *out, int N, int H, int W, in
   subsample_kernel<<<hd::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N,
                                                                              H, W, C / 4, Ho, Wo, stride);
   return hd::check_launch("subsample_kernel");
+}
+
+extern "C" int hd_groupnorm_relu_split(const float *x, const float *gamma, const float *beta, void *out_hi, void *out_lo, int B, int T, int C,
+                                       int groups, float eps, void *stream) {
+  HD_REQUIRE(x && gamma && beta && out_hi && out_lo && B > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && T * (C / groups) <= 40 * 32,
+             "hd_groupnorm_relu_split: bad arguments (T * C/groups must be <= 1280)");
+  groupnorm_relu_split_kernel<<<hd::ceil_div((long long)B * groups, 4), 128, 0, (cudaStream_t)stream>>>(
+      x, gamma, beta, reinterpret_cast<__half *>(out_hi), reinterpret_cast<__half *>(out_lo), B, T, C, groups, eps);
+  return hd::check_launch("groupnorm_relu_split_kernel");
+}
+
+extern "C" int hd_split_f16(const float *x, void *hi, void *lo, long long n, void *stream) {
+  HD_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0 && hd::aligned16(x) && hd::aligned16(hi) && hd::aligned16(lo), "hd_split_f16: bad arguments");
+  split_f16_kernel<<<hd::ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<uint2 *>(hi),
+                                                                              reinterpret_cast<uint2 *>(lo), n / 4);
+  return hd::check_launch("split_f16_kernel");
+}
+
+extern "C" int hd_ief_fc1_theta(const float *P, const float *theta, int theta_ld, const float *W, int K, int C, void *out_hi, void *out_lo,
+                                float *out_f32, int N, void *stream) {
+  HD_REQUIRE(P && theta && W && (out_hi || out_f32) && ((out_hi == nullptr) == (out_lo == nullptr)) && N > 0 && K > 0 && K <= 96 && theta_ld >= K &&
+                 C > 0 && C % 4 == 0 && hd::aligned16(P) && hd::aligned16(W) && (!out_hi || (hd::aligned16(out_hi) && hd::aligned16(out_lo))) &&
+                 (!out_f32 || hd::aligned16(out_f32)),
+             "hd_ief_fc1_theta: bad arguments");
+  ief_fc1_theta_kernel<<<hd::ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(P, theta, theta_ld, W, K, C, reinterpret_cast<__half *>(out_hi),
+                                                                            reinterpret_cast<__half *>(out_lo), out_f32, N);
+  return hd::check_launch("ief_fc1_theta_kernel");
+}
+
+extern "C" int hd_ief_fc3(const float *h2, const float *W, const float *bias, const float *prev, int prev_ld, float *out, int out_ld, int N,
+                          int K, int D, void *stream) {
+  HD_REQUIRE(h2 && W && bias && prev && out && N > 0 && K > 0 && K % 8 == 0 && D > 0 && D <= 96 && prev_ld >= D && out_ld >= D,
+             "hd_ief_fc3: bad arguments (K % 8 == 0, D <= 96)");
+  const size_t smem = (size_t)(8 * K + 8 * 8 * 96) * sizeof(float);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev] && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ief_fc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) { hd::set_last_error("ief_fc3 attr", e); return HD_ERR_CUDA; }
+    configured[dev] = true;
+  }
+  HD_REQUIRE(smem <= 100 * 1024, "hd_ief_fc3: K too large");
+  ief_fc3_kernel<<<hd::ceil_div(N, 8), 256, smem, (cudaStream_t)stream>>>(h2, W, bias, prev, prev_ld, out, out_ld, N, K, D);
+  return hd::check_launch("ief_fc3_kernel");
 }

@@ -248,6 +248,7 @@ class ConvOp(object):
             check(rc, 'hd_conv_gemm')
 
 
+FAST_HEADS = os.environ.get('HD_FAST_HEADS', '1') != '0'          # A/B switch: f_movie / IEF through the pre-split + small-GEMM kernels
 CONV1_PLANES = os.environ.get('HD_CONV1_PLANES', '1') != '0'      # A/B switch: conv1 from padded fp16 planes vs fp32 row-segment gather
 
 
@@ -556,7 +557,29 @@ class FMoviePlan(object):
         self.impl = impl
         self._bound_for = None
 
+    def _bind_fast(self, x):
+        """impl auto / tc3h: GroupNorm + ReLU + split in one kernel (hd_groupnorm_relu_split), then the temporal conv reads its A
+        operand as the pre-split pair (cp.async producer, TMA epilogue) -- the register-staged GN prologue path ran at ~1/4 of
+        that speed (profiles/r02_launches_step_c3_before_heads.csv: 248 us per conv at 640 rows)."""
+        dev, Cc = self.p.device, self.p.C
+        B, T = self.B, self.T
+        if not hasattr(self, 'act'):
+            self.act = (torch.empty((B * T, Cc), dtype=torch.float16, device=dev), torch.empty((B * T, Cc), dtype=torch.float16, device=dev))
+        steps, cur = [], x
+        for i, blk in enumerate(self.p.blocks):
+            out = self.bufs[i % 2]
+            steps.append(('gns', cur, blk['gn1']))
+            steps.append(('conv', blk['conv1'].bind(None, B, T, 1, self.mid, inp_split=self.act, impl=self.impl)))
+            steps.append(('gns', self.mid, blk['gn2']))
+            steps.append(('conv', blk['conv2'].bind(None, B, T, 1, out, inp_split=self.act, res=cur, res_geom=(Cc, T, 1, 1), impl=self.impl)))
+            cur = out
+        self.steps, self.out = steps, cur
+        self._bound_for = x.data_ptr()
+
     def _bind(self, x):
+        if self.impl in ('auto', 'tc3h') and self.p.blocks and all(b[k].tc == 'f16' for b in self.p.blocks for k in ('conv1', 'conv2')) \
+                and self.T * (self.p.C // GN_GROUPS) <= 1280 and FAST_HEADS:
+            return self._bind_fast(x)
         steps = []
         cur = x
         pre = (self.gain, self.offset, self.p.C, 1)
@@ -581,6 +604,10 @@ class FMoviePlan(object):
             if s[0] == 'gn':
                 check(lib.hd_groupnorm_stats(fptr(s[1]), fptr(s[2][0]), fptr(s[2][1]), fptr(self.gain), fptr(self.offset),
                                              self.B, self.T, self.p.C, GN_GROUPS, GN_EPS, st), 'hd_groupnorm_stats')
+            elif s[0] == 'gns':
+                check(lib.hd_groupnorm_relu_split(fptr(s[1]), fptr(s[2][0]), fptr(s[2][1]), C.c_void_p(self.act[0].data_ptr()),
+                                                  C.c_void_p(self.act[1].data_ptr()), self.B, self.T, self.p.C, GN_GROUPS, GN_EPS, st),
+                      'hd_groupnorm_relu_split')
             else:
                 s[1].run(st)
         return self.out
@@ -638,9 +665,49 @@ class IEFPlan(object):
         self.delta_out = {dt: self.delta_all[:, i, :] for i, dt in enumerate(self.delta_keys)}
         self.impl = impl
         self._bound_for = None
+        heads = [packed.main] + [packed.deltas[k] for k in self.delta_keys]
+        self.fast = FAST_HEADS and impl in ('auto', 'tc3h') and all(h.fc1_phi.tc == 'f16' and h.fc2.tc == 'f16' for h in heads)
+        if self.fast:
+            f16 = dict(dtype=torch.float16, device=dev)
+            self.phi_split = (torch.empty((N, heads[0].feat), **f16), torch.empty((N, heads[0].feat), **f16))
+            self.h1_split = (torch.empty((N, 1024), **f16), torch.empty((N, 1024), **f16))
+
+    def _head_ops_fast(self, head, start_view, state_view, ld):
+        """impl auto / tc3h.  phi arrives once as a pre-split pair (hd_split_f16); per stage: hd_ief_fc1_theta (K = 85 / 72, writes h1
+        pre-split) -> fc2 on the tensor cores (cp.async producer, TMA epilogue) -> hd_ief_fc3 (D = 85 / 72 + the IEF update).  The
+        generic kernels ran fc1-theta on 40 SIMT blocks (50 us) and fc3 as ONE 128-row tile per 128 poses on 5 CTAs (80 us)."""
+        N = self.N
+        ops = [('conv', head.fc1_phi.bind(None, N, 1, 1, self.P, inp_split=self.phi_split, impl=self.impl))]
+        for s in range(self.num_stage):
+            prev = start_view if s == 0 else state_view
+            prev_ld = start_view.stride(0) if s == 0 else ld
+            ops.append(('fc1t', prev, prev_ld, head))
+            ops.append(('conv', head.fc2.bind(None, N, 1, 1, self.h2, inp_split=self.h1_split, impl=self.impl)))
+            ops.append(('fc3', prev, prev_ld, state_view, ld, head))
+        return ops
+
+    def _run_ops(self, ops, st):
+        N = self.N
+        for op in ops:
+            kind = op[0] if isinstance(op, tuple) else None
+            if kind is None:
+                op.run(st)
+            elif kind == 'conv':
+                op[1].run(st)
+            elif kind == 'fc1t':
+                _, prev, prev_ld, head = op
+                check(lib.hd_ief_fc1_theta(fptr(self.P), fptr(prev), prev_ld, fptr(head.fc1_theta.w_kn), head.d, 1024,
+                                           C.c_void_p(self.h1_split[0].data_ptr()), C.c_void_p(self.h1_split[1].data_ptr()), None, N, st),
+                      'hd_ief_fc1_theta')
+            else:
+                _, prev, prev_ld, out, out_ld, head = op
+                check(lib.hd_ief_fc3(fptr(self.h2), fptr(head.fc3.w_kn), fptr(head.fc3.post_shift), fptr(prev), prev_ld, fptr(out), out_ld, N,
+                                     1024, head.d, st), 'hd_ief_fc3')
 
     def _head_ops(self, head, phi, start_view, state_view, ld):
         """ops for one hmr_ief: start_view = theta_prev of stage 0, state_view = in-place theta afterwards."""
+        if self.fast:
+            return self._head_ops_fast(head, start_view, state_view, ld)
         N = self.N
         ops = [head.fc1_phi.bind(phi, N, 1, 1, self.P, impl=self.impl)]
         for s in range(self.num_stage):
@@ -664,8 +731,10 @@ class IEFPlan(object):
         st = current_stream() if stream is None else stream
         if self._bound_for != (phi.data_ptr(), theta0.data_ptr()):
             self._bind(phi, theta0)
-        for op in self.main_ops:
-            op.run(st)
+        if self.fast:
+            check(lib.hd_split_f16(fptr(phi), C.c_void_p(self.phi_split[0].data_ptr()), C.c_void_p(self.phi_split[1].data_ptr()),
+                                   phi.numel(), st), 'hd_split_f16')
+        self._run_ops(self.main_ops, st)
         return self.theta
 
     def run_deltas(self, stream=None):
@@ -674,8 +743,7 @@ class IEFPlan(object):
         for dt in self.delta_keys:
             check(lib.hd_ief_delta_init(fptr(self.theta), fptr(self.delta_out[dt]), self.delta_out[dt].stride(0), self.N, st),
                   'hd_ief_delta_init')
-            for op in self.delta_ops[dt]:
-                op.run(st)
+            self._run_ops(self.delta_ops[dt], st)
         return self.delta_out
 
     def run(self, phi, theta0, stream=None):
@@ -686,7 +754,7 @@ class IEFPlan(object):
     @property
     def num_launches(self):
         per = 1 + 3 * self.num_stage
-        return per + len(self.delta_keys) * (per + 1)
+        return per + len(self.delta_keys) * (per + 1) + (1 if self.fast else 0)
 
 
 def run_ief_head(head: PackedIEFHead, phi, start, num_stage=3, impl='auto', stream=None, out=None):

@@ -161,6 +161,7 @@ class SMPLConstants(object):
             self.w_hi = torch.from_numpy(w_hi).to(dev)
             self.w_lo = torch.from_numpy((wd - w_hi.astype(np.float32)).astype(np.float16)).to(dev)
         self.lbs_tc = bool(tc) and os.environ.get('HD_LBS_TC', '1') != '0' and (V * 3 * 4) % 8 == 0
+        self.lbs_tc_min_batch = int(os.environ.get('HD_LBS_TC_MIN', '2368'))         # 148 SMs x 16 poses
 
     def workspace(self, N):
         need = int(lib.hd_smpl_workspace_bytes(N))
@@ -217,8 +218,10 @@ class SMPLConstants(object):
             vpos = torch.empty((N, self.vp_ld), **f32)
             a12 = torch.empty((N, 288), **f32)
             rsw = torch.empty((N, 216), **f32)
+            # tensor-core skinning walks 16-pose batches, one CTA per batch at a time: below ~148 batches the CUDA-core kernel (one
+            # CTA per 16 poses x 128 vertices) fills the chip better (640 poses: 56 us vs 100 us)
             a12t = (torch.empty((N, 12, 32), dtype=torch.float16, device=dev), torch.empty((N, 12, 32), dtype=torch.float16, device=dev)) \
-                if self.lbs_tc else None
+                if (self.lbs_tc and N >= self.lbs_tc_min_batch) else None
             # operand rows arrive pre-split from the pose kernel: cp.async producer + TMA-store epilogue (K = 256)
             op = self.blend.bind(None, N, 1, 1, vpos, inp_split=coef, impl='tc3h')
             self._tc_bufs[N] = (coef, vpos, a12, rsw, op, a12t)

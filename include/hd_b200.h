@@ -141,6 +141,22 @@ int hd_process_image(const unsigned char *frames, int N, int H, int W, const int
 int hd_groupnorm_stats(const float *x, const float *gamma, const float *beta, float *gain, float *offset,
                        int B, int T, int C, int groups, float eps, void *stream);
 
+/* GroupNorm + ReLU straight to the tensor-core conv's A operand format: y = relu(group_norm(x)) as an fp16 head / 2^11-scaled
+ * remainder pair [B*T, C] (same statistics and affine as hd_groupnorm_stats + the conv prologue).  T * C/groups <= 1280. */
+int hd_groupnorm_relu_split(const float *x, const float *gamma, const float *beta, void *out_hi, void *out_lo, int B, int T, int C,
+                            int groups, float eps, void *stream);
+/* fp32 [n] -> fp16 head / remainder pair (n % 4 == 0, 16-byte aligned). */
+int hd_split_f16(const float *x, void *hi, void *lo, long long n, void *stream);
+
+/* ---- IEF pieces too small / too narrow for the tensor-core tile (src/models.py:101-113,400-413) ----
+ * fc1, theta part: h1 = relu(P + theta . W) with P [N,C] = phi . W1[:2048] + b1 (hoisted), theta rows of K <= 96 at stride theta_ld,
+ * W [K,C]; writes h1 as an fp16 head / remainder pair (fc2's A operand) and / or fp32. */
+int hd_ief_fc1_theta(const float *P, const float *theta, int theta_ld, const float *W, int K, int C, void *out_hi, void *out_lo,
+                     float *out_f32, int N, void *stream);
+/* fc3 + IEF update: out[n, :D] = prev[n, :D] + h2[n] . W + bias, h2 [N,K] (K % 8 == 0), W [K,D], D <= 96; fixed summation order. */
+int hd_ief_fc3(const float *h2, const float *W, const float *bias, const float *prev, int prev_ld, float *out, int out_ld, int N, int K,
+               int D, void *stream);
+
 /* ---- IEF glue (src/models.py:349-371): dst[n*dst_ld + :85] = [1, 0, 0, theta[n,3:75], theta[n,75:85]] ---- */
 int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *stream);
 

@@ -13,9 +13,11 @@ def rel_err(a, b):
     return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
 
 
-def _run(model, beta, theta, cam=None, joint_type='cocoplus', tc=True):
+def _run(model, beta, theta, cam=None, joint_type='cocoplus', tc=True, lbs_tc_min=None):
     from human_dynamics_b200.smpl import SMPLConstants
     c = SMPLConstants(model, joint_type=joint_type, tc=tc)
+    if lbs_tc_min is not None:
+        c.lbs_tc_min_batch = lbs_tc_min
     o = c.forward(torch.from_numpy(beta).cuda(), torch.from_numpy(theta).cuda(),
                   cam=None if cam is None else torch.from_numpy(cam).cuda())
     torch.cuda.synchronize()
@@ -47,15 +49,17 @@ def test_smpl_forward_matches_oracle(smpl_model, n, zero_pose):
         assert np.array_equal(got['Rs'], np.tile(np.eye(3, dtype=np.float32), (n, 24, 1, 1)))
 
 
+@pytest.mark.parametrize('lbs_tc', [False, True])
 @pytest.mark.parametrize('n', [256, 777])
-def test_smpl_tensor_core_blend_path(smpl_model, smpl_model_dense, n):
+def test_smpl_tensor_core_blend_path(smpl_model, smpl_model_dense, n, lbs_tc):
     """N >= 256 takes the staged path (pose -> tcgen05 blend GEMM -> skinning -> keypoints); must agree with the oracle
-    and, to rounding, with the fused FP32 kernel."""
+    and, to rounding, with the fused FP32 kernel.  lbs_tc: skinning on the tensor cores (smpl_lbs_tc.cu; by default only for
+    batches that fill the chip) vs the CUDA-core skinning kernel."""
     from human_dynamics_b200 import synthetic
     for model, jt in ((smpl_model, 'cocoplus'), (smpl_model_dense, 'lsp')):
         beta, theta = synthetic.make_smpl_inputs(n, seed=n)
         cam = np.random.RandomState(n).uniform(0.5, 1.5, size=(n, 3)).astype(np.float32)
-        got = _run(model, beta, theta, cam, joint_type=jt)
+        got = _run(model, beta, theta, cam, joint_type=jt, lbs_tc_min=0 if lbs_tc else 1 << 30)
         ref = _oracle(model, beta, theta, cam, joint_type=jt)
         fused = _run(model, beta, theta, cam, joint_type=jt, tc=False)
         for k in ('verts', 'joints', 'Rs', 'Jtr', 'kps'):
