@@ -172,3 +172,28 @@ def test_batch_rot2aa_matches_oracle():
     big = (nrm > 0.3) & (nrm < 3.0)                  # beyond pi the axis-angle vector of the same rotation is a different one
     assert np.abs(aa[big] - th[big]).max() < 2e-5
     assert np.all(aa[::50] == 0.0)
+
+
+def test_smpl_tensor_core_skinning_into_delta_slots(smpl_model):
+    """smpl_lbs_tc with the [B,T,D,...] in-place stacking (pose n -> slot n*D + d, odd slots are only 8-byte aligned) and strided
+    omega views, ragged last batch / last vertex tile."""
+    from human_dynamics_b200.smpl import SMPLConstants
+    n, D = 300, 3
+    rng = np.random.RandomState(1)
+    omega = rng.normal(0, 0.3, size=(n, 85)).astype(np.float32)
+    om = torch.from_numpy(omega).cuda()
+    c = SMPLConstants(smpl_model)
+    c.lbs_tc_min_batch = 0
+    V, K = c.num_verts, c.num_kps
+    out = {'verts': torch.zeros((n * D, V, 3), device='cuda'), 'joints': torch.zeros((n * D, K, 3), device='cuda'),
+           'Rs': torch.zeros((n * D, 24, 3, 3), device='cuda'), 'Jtr': torch.zeros((n * D, 24, 3), device='cuda'),
+           'kps': torch.zeros((n * D, K, 2), device='cuda')}
+    ref = _oracle(smpl_model, omega[:, 75:85], omega[:, 3:75], omega[:, :3])
+    for d in (1, 2):
+        c.forward(om[:, 75:85], om[:, 3:75], cam=om[:, 0:3], out=out, slot=(D, d))
+    torch.cuda.synchronize()
+    v = out['verts'].cpu().numpy().reshape(n, D, V, 3)
+    assert np.all(v[:, 0] == 0)
+    for d in (1, 2):
+        assert rel_err(v[:, d], ref['verts']) < REL
+    assert np.array_equal(v[:, 1], v[:, 2])
