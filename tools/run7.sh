@@ -9,5 +9,5 @@ timeout 600 python bench.py --steps 5 > gpurun_out/r7_bench.json 2> gpurun_out/r
 tail -c 1300 gpurun_out/r7_bench.json; tail -3 gpurun_out/r7_bench.err
 HD_FAST_HEADS=0 timeout 300 python bench.py --steps 5 --no-cpu-baseline --no-extra > gpurun_out/r7_bench_slowheads.json 2>/dev/null; head -c 220 gpurun_out/r7_bench_slowheads.json; echo
 run 200 layers python tools/layer_table.py
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 181 -c 181 --csv --log-file gpurun_out/r7_launches_step.csv python tools/prof_step.py 2 > gpurun_out/r7_launches.log 2>&1; tail -2 gpurun_out/r7_launches.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 200 --csv --log-file gpurun_out/r7_launches_step.csv python tools/prof_step.py 2 > gpurun_out/r7_launches.log 2>&1; tail -2 gpurun_out/r7_launches.log
 HD_SPLIT=1 timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_gemm_tc -s 2 -c 1 -f -o gpurun_out/r7_tepi_k2304 python tools/prof_one.py 640 14 256 256 3 0 > gpurun_out/r7_ncu2.log 2>&1; tail -2 gpurun_out/r7_ncu2.log
