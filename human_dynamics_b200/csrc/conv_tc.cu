@@ -818,8 +818,11 @@ int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
     configured[dev] = true;
   }
   alignas(64) CUtensorMap thi, tlo;
-  memcpy(&thi, d->tmap_hi, sizeof(CUtensorMap));
-  memcpy(&tlo, d->tmap_lo ? d->tmap_lo : d->tmap_hi, sizeof(CUtensorMap));
+  // weight maps whose box matches this tile width: the 64-row variants serve wide layers run with 64-wide tiles (few-tile GEMMs)
+  const bool n64 = BN == 64 && p.Cout > 64;
+  const void *mhi = n64 ? d->tmap_hi_n64 : d->tmap_hi, *mlo = n64 ? d->tmap_lo_n64 : d->tmap_lo;
+  memcpy(&thi, mhi, sizeof(CUtensorMap));
+  memcpy(&tlo, mlo ? mlo : mhi, sizeof(CUtensorMap));
   alignas(64) EpiMaps em;
   if (TEPI) {      // absent maps are never dereferenced by the kernel (guarded by the same null tests on p.res / p.out / p.out_hi)
     const void *any = d->tmap_out ? d->tmap_out : d->tmap_out_hi;
@@ -873,8 +876,16 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       const bool res_plain = !p.res || (p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo);
       const bool maps = (!p.res || d->tmap_res) && (!p.out || d->tmap_out) && (!p.out_hi || (d->tmap_out_hi && d->tmap_out_lo));
       if (maps && res_plain && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE) && (p.K <= 256 || p.K <= tepi_maxk))
-        return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, false, true>(p, d, st)
-                            : launch_tc<128, true, 4, true, false, true, false, true>(p, d, st);
+      {
+        // few-tile GEMMs (IEF FCs at 640 rows: 40 tiles of 128x128 for 148 SMs): 64-wide tiles double the CTA count
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tiles128 = ceil_div(p.M, BM) * ceil_div(p.Cout, 128);
+        const bool narrow = p.Cout <= 64 || (d->tmap_hi_n64 && d->tmap_lo_n64 && p.Cout % 64 == 0 && 2 * tiles128 <= sms);
+        return narrow ? launch_tc<64, true, 4, true, false, true, false, true>(p, d, st)
+                      : launch_tc<128, true, 4, true, false, true, false, true>(p, d, st);
+      }
     }
     if (p.K <= 256)      // (strided-subsample residuals / no tensor maps) two drain/epilogue warp groups with per-thread global accesses
       return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);

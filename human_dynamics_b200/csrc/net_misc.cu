@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(128) groupnorm_relu_split_kernel(const float *
 #pragma unroll
   for (int e = 0; e < MAXE; ++e) {
     const int i = lane + 32 * e;
-    v[e] = i < cnt ? __ldg(x + base + (size_t)(i / cg) * C + (i % cg)) : 0.f;
+    // element i of the group = (row i / cg, channel i % cg); cg == 64 (f_movie: 2048 / 32) makes that (e >> 1, lane + 32 (e & 1))
+    const size_t off = cg == 64 ? (size_t)(e >> 1) * C + (lane + 32 * (e & 1)) : (size_t)(i / cg) * C + (i % cg);
+    v[e] = i < cnt ? __ldg(x + base + off) : 0.f;
     if (i < cnt) s += v[e];
   }
 #pragma unroll
@@ -206,13 +208,14 @@ __global__ void __launch_bounds__(128) groupnorm_relu_split_kernel(const float *
   for (int e = 0; e < MAXE; ++e) {
     const int i = lane + 32 * e;
     if (i >= cnt) continue;
-    const int ch = g * cg + (i % cg);
+    const int cin = cg == 64 ? lane + 32 * (e & 1) : i % cg;
+    const int ch = g * cg + cin;
     const float gn = rstd * __ldg(gamma + ch);
     const float off = __ldg(beta + ch) - mean * gn;
     const float y = fmaxf(v[e] * gn + off, 0.f);
     uint32_t h, l;
     hd::split_f16x2(y, 0.f, h, l);
-    const size_t o = base + (size_t)(i / cg) * C + (i % cg);
+    const size_t o = base + (cg == 64 ? (size_t)(e >> 1) * C : (size_t)(i / cg) * C) + cin;
     out_hi[o] = __ushort_as_half((unsigned short)(h & 0xffffu));
     out_lo[o] = __ushort_as_half((unsigned short)(l & 0xffffu));
   }
@@ -239,21 +242,27 @@ __global__ void __launch_bounds__(256) ief_fc1_theta_kernel(const float *__restr
                                                             __half *__restrict__ out_lo, float *__restrict__ out_f32, int N) {
   __shared__ float th[8][96];
   const int r0 = blockIdx.x * 8;
-  for (int i = threadIdx.x; i < 8 * K; i += 256) {
-    const int r = i / K, k = i - r * K;
-    th[r][k] = (r0 + r < N) ? __ldg(theta + (size_t)(r0 + r) * theta_ld + k) : 0.f;
+  for (int i = threadIdx.x; i < 8 * 96; i += 256) {
+    const int r = i / 96, k = i - r * 96;
+    th[r][k] = (r0 + r < N && k < K) ? __ldg(theta + (size_t)(r0 + r) * theta_ld + k) : 0.f;
   }
   __syncthreads();
   for (int c = threadIdx.x * 4; c < Cc; c += 1024) {
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-    for (int k = 0; k < K; ++k) {
-      const float4 w = __ldg(reinterpret_cast<const float4 *>(W + (size_t)k * Cc + c));
+    for (int k0 = 0; k0 < K; k0 += 8) {          // 8 weight rows in flight: the loop is L2-latency-, not FMA-bound otherwise
+      float4 w[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float t = th[r][k];
-        acc[r][0] += t * w.x; acc[r][1] += t * w.y; acc[r][2] += t * w.z; acc[r][3] += t * w.w;
+      for (int u = 0; u < 8; ++u)
+        w[u] = (k0 + u < K) ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)(k0 + u) * Cc + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float t = th[r][k0 + u];           // zero beyond K (th is 96 wide, K <= 96)
+          acc[r][0] += t * w[u].x; acc[r][1] += t * w[u].y; acc[r][2] += t * w[u].z; acc[r][3] += t * w[u].w;
+        }
       }
     }
 #pragma unroll
@@ -296,13 +305,20 @@ __global__ void __launch_bounds__(256) ief_fc3_kernel(const float *__restrict__ 
   for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.f;
   const int kper = K / 8;
   const bool c1 = lane + 32 < D, c2 = lane + 64 < D;
-  for (int k = warp * kper; k < (warp + 1) * kper; ++k) {
-    const float *wr = W + (size_t)k * D;
-    const float w0 = __ldg(wr + lane), w1 = c1 ? __ldg(wr + lane + 32) : 0.f, w2 = c2 ? __ldg(wr + lane + 64) : 0.f;
+  for (int k0 = warp * kper; k0 < (warp + 1) * kper; k0 += 8) {       // (kper % 8 == 0 is required by the host entry)
+    float w0[8], w1[8], w2[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float h = hs[r * K + k];
-      acc[r][0] += h * w0; acc[r][1] += h * w1; acc[r][2] += h * w2;
+    for (int u = 0; u < 8; ++u) {
+      const float *wr = W + (size_t)(k0 + u) * D;
+      w0[u] = __ldg(wr + lane); w1[u] = c1 ? __ldg(wr + lane + 32) : 0.f; w2[u] = c2 ? __ldg(wr + lane + 64) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float h = hs[r * K + k0 + u];
+        acc[r][0] += h * w0[u]; acc[r][1] += h * w1[u]; acc[r][2] += h * w2[u];
+      }
     }
   }
 #pragma unroll
@@ -444,8 +460,8 @@ extern "C" int hd_ief_fc1_theta(const float *P, const float *theta, int theta_ld
 
 extern "C" int hd_ief_fc3(const float *h2, const float *W, const float *bias, const float *prev, int prev_ld, float *out, int out_ld, int N,
                           int K, int D, void *stream) {
-  HD_REQUIRE(h2 && W && bias && prev && out && N > 0 && K > 0 && K % 8 == 0 && D > 0 && D <= 96 && prev_ld >= D && out_ld >= D,
-             "hd_ief_fc3: bad arguments (K % 8 == 0, D <= 96)");
+  HD_REQUIRE(h2 && W && bias && prev && out && N > 0 && K > 0 && K % 64 == 0 && D > 0 && D <= 96 && prev_ld >= D && out_ld >= D,
+             "hd_ief_fc3: bad arguments (K % 64 == 0, D <= 96)");
   const size_t smem = (size_t)(8 * K + 8 * 8 * 96) * sizeof(float);
   static bool configured[64] = {};
   int dev = 0;

@@ -112,6 +112,11 @@ class PackedConv(object):
                   'hd_make_weight_tmap')
             check(lib.hd_make_weight_tmap(C.c_void_p(self.w_nk_lo.data_ptr()), rows, self.K_pad, box, eb, C.cast(self.tmap_lo, C.c_void_p)),
                   'hd_make_weight_tmap')
+            self.tmap_hi64 = self.tmap_lo64 = None
+            if want == 'f16' and box == 128 and self.Cout % 64 == 0:      # 64-row boxes: few-tile GEMMs run on 64-wide tiles
+                self.tmap_hi64, self.tmap_lo64 = (C.c_ubyte * 128)(), (C.c_ubyte * 128)()
+                for t, m in ((self.w_nk_hi, self.tmap_hi64), (self.w_nk_lo, self.tmap_lo64)):
+                    check(lib.hd_make_weight_tmap(C.c_void_p(t.data_ptr()), rows, self.K_pad, 64, eb, C.cast(m, C.c_void_p)), 'hd_make_weight_tmap')
             self.tc = want
 
     def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto',
@@ -171,6 +176,9 @@ class PackedConv(object):
             d.w_nk_hi, d.w_nk_lo = self.w_nk_hi.data_ptr(), self.w_nk_lo.data_ptr()
             d.tmap_hi = C.cast(self.tmap_hi, C.c_void_p)
             d.tmap_lo = C.cast(self.tmap_lo, C.c_void_p)
+            if getattr(self, 'tmap_hi64', None) is not None:
+                d.tmap_hi_n64 = C.cast(self.tmap_hi64, C.c_void_p)
+                d.tmap_lo_n64 = C.cast(self.tmap_lo64, C.c_void_p)
         else:
             d.impl = _lib.HD_IMPL_SIMT
         op = ConvOp(d, (self, inp, out, pre, res, inp_split, out_split, post2), (Ho, Wo))

@@ -85,6 +85,9 @@ typedef struct {
    * HD_CONV_NO_TMA_EPILOGUE in `flags`) the epilogue uses per-thread global accesses.  Results are identical. */
   const void *tmap_res, *tmap_out, *tmap_out_hi, *tmap_out_lo;
   int flags;
+  /* optional second pair of weight maps with a 64-row box (hd_make_weight_tmap(..., box_rows = 64, ...)) for Cout > 64: lets a GEMM
+   * with few 128x128 tiles (2 * tiles <= #SMs) run on 64-wide tiles, i.e. on twice as many CTAs. */
+  const void *tmap_hi_n64, *tmap_lo_n64;
 } hd_conv_desc;
 
 enum {
@@ -153,7 +156,7 @@ int hd_split_f16(const float *x, void *hi, void *lo, long long n, void *stream);
  * W [K,C]; writes h1 as an fp16 head / remainder pair (fc2's A operand) and / or fp32. */
 int hd_ief_fc1_theta(const float *P, const float *theta, int theta_ld, const float *W, int K, int C, void *out_hi, void *out_lo,
                      float *out_f32, int N, void *stream);
-/* fc3 + IEF update: out[n, :D] = prev[n, :D] + h2[n] . W + bias, h2 [N,K] (K % 8 == 0), W [K,D], D <= 96; fixed summation order. */
+/* fc3 + IEF update: out[n, :D] = prev[n, :D] + h2[n] . W + bias, h2 [N,K] (K % 64 == 0), W [K,D], D <= 96; fixed summation order. */
 int hd_ief_fc3(const float *h2, const float *W, const float *bias, const float *prev, int prev_ld, float *out, int out_ld, int N, int K,
                int D, void *stream);
 
