@@ -42,11 +42,14 @@ using namespace ptx;
 // TEPI (TMA epilogue; K <= 256, i.e. the HBM-shaped 1x1 layers): one drain group whose threads own accumulator rows and
 // only ever touch shared memory; the residual arrives and fp32 / fp16-pair outputs leave as 128-row x 32-column slabs
 // moved by TMA (cp.async.bulk.tensor load / store) through a ring of three swizzled staging buffers.
-template <int BN, bool HALF, bool DUAL = false, bool TEPI = false>
+template <int BN, bool HALF, bool DUAL = false, int TEPI = 0>
 struct Cfg {
   // DUAL (epilogue-bound layers, K <= 256, one drain group per tile): two drain/epilogue warp groups take alternate tiles;
   // the main loop is short there, so 2 operand stages suffice and pay for the second set of staging tiles.
-  static constexpr int STAGES = (DUAL || TEPI) ? 2 : 3;
+  // TEPI 1: full staging ring (fp32 residual / output + fp16 pair), 2 operand stages.  TEPI 2: layers that write ONLY the fp16 pair
+  // and add no residual (conv1 / conv2 of a bottleneck: long K, tensor-bound): 16 KB slabs, one buffer per drain group, which leaves
+  // room for the third operand stage their main loop wants.
+  static constexpr int STAGES = (DUAL || TEPI == 1) ? 2 : 3;
   static constexpr int DW = (DUAL || TEPI) ? 8 : 4;             // drain + epilogue warps (DUAL: two groups on alternate tiles;
                                                                 // TEPI: two groups on alternate 32-column slabs of the same tile)
   static constexpr int NUM_THREADS = (DW + 8 + 4) * 32;         // + 8 producer warps + {TMA, MMA, 2 idle}
@@ -62,8 +65,8 @@ struct Cfg {
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
   // TEPI staging ring: per buffer one fp32 slab [128][32] (128-byte rows, SWIZZLE_128B) + two fp16 slabs [128][32]
   // (64-byte rows, SWIZZLE_64B); 1024-byte aligned
-  static constexpr int EPI_NB = 3;
-  static constexpr int EPI_F32_BYTES = 128 * 128, EPI_H_BYTES = 128 * 64;
+  static constexpr int EPI_NB = TEPI == 2 ? 2 : 3;
+  static constexpr int EPI_F32_BYTES = TEPI == 2 ? 0 : 128 * 128, EPI_H_BYTES = 128 * 64;
   static constexpr int EPI_BUF_BYTES = EPI_F32_BYTES + 2 * EPI_H_BYTES;
   static constexpr int EPI_OFFSET = (BAR_OFFSET + 128 + 1023) / 1024 * 1024;
   static constexpr int SMEM_BYTES = TEPI ? EPI_OFFSET + EPI_NB * EPI_BUF_BYTES + 1024 : LUT_OFFSET + 1024 + 1024;   // + alignment slack
@@ -83,7 +86,7 @@ struct EpiMaps {      // TEPI only: activation tensor maps (fp32 residual / outp
   CUtensorMap res, out, ohi, olo;
 };
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT, bool DUAL, bool TEPI>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER, bool ASPLIT, bool DUAL, int TEPI>
 __global__ void __launch_bounds__((Cfg<BN, HALF, DUAL, TEPI>::NUM_THREADS), 1)
 conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
                     const __grid_constant__ EpiMaps em) {
@@ -800,7 +803,7 @@ EncodeTiledFn get_encode_fn() {
 
 constexpr int kMaxDevices = 64;
 
-template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false, bool DUAL = false, bool TEPI = false>
+template <int BN, bool SPLIT, int PCH, bool HALF, bool GATHER = false, bool ASPLIT = false, bool DUAL = false, int TEPI = 0>
 int launch_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) {
   using C = Cfg<BN, HALF, DUAL, TEPI>;
   // function attributes and the SM count are per device: a process may drive several GPUs through this library
@@ -860,7 +863,7 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       return HD_ERR_INVALID;
     }
     const bool maps = p.out && d->tmap_out && !p.res && !p.out_hi;
-    if (maps && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE)) return launch_tc<64, true, 4, true, false, true, false, true>(p, d, st);
+    if (maps && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE)) return launch_tc<64, true, 4, true, false, true, false, 1>(p, d, st);
     return launch_tc<64, true, 4, true, false, true, true>(p, d, st);
   }
   if (p.in_hi) {                       // pre-split fp16 activations: cp.async producer
@@ -883,8 +886,12 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int tiles128 = ceil_div(p.M, BM) * ceil_div(p.Cout, 128);
         const bool narrow = p.Cout <= 64 || (d->tmap_hi_n64 && d->tmap_lo_n64 && p.Cout % 64 == 0 && 2 * tiles128 <= sms);
-        return narrow ? launch_tc<64, true, 4, true, false, true, false, true>(p, d, st)
-                      : launch_tc<128, true, 4, true, false, true, false, true>(p, d, st);
+        static const bool slim_ok = [] { const char *e = getenv("HD_TEPI_SLIM"); return !e || atoi(e) != 0; }();
+        if (slim_ok && !p.res && !p.out && p.out_hi && p.K > 256)     // split-only, long K: 3 operand stages + slim ring
+          return narrow ? launch_tc<64, true, 4, true, false, true, false, 2>(p, d, st)
+                        : launch_tc<128, true, 4, true, false, true, false, 2>(p, d, st);
+        return narrow ? launch_tc<64, true, 4, true, false, true, false, 1>(p, d, st)
+                      : launch_tc<128, true, 4, true, false, true, false, 1>(p, d, st);
       }
     }
     if (p.K <= 256)      // (strided-subsample residuals / no tensor maps) two drain/epilogue warp groups with per-thread global accesses
