@@ -588,7 +588,7 @@ def measure_roofline(args, peaks, env):
         reps = N // c
         evs = []
         torch.cuda.synchronize()
-        for op in plan.ops:
+        for op in ([plan.conv1_op] if getattr(plan, 'conv1_op', None) is not None else []) + list(plan.ops):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); op.run(stp); b.record()
             evs.append((a, b, op))
@@ -597,7 +597,8 @@ def measure_roofline(args, peaks, env):
             d = op.d
             if d is None:                 # not a conv (strided-shortcut subsample)
                 continue
-            fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
+            kdim = 147 if (d.flags & 2) else d.KH * d.KW * d.Cin          # conv1 over padded planes: the 7x7x3 taps, not the padded K = 256
+            fl = 2.0 * d.n_img * d.Ho * d.Wo * d.Cout * kdim
             t = a.elapsed_time(b) * 1e-3
             conv_time += t * reps
             if d.impl != _lib.HD_IMPL_SIMT or args.mode == 'simt':
