@@ -420,6 +420,25 @@ def main():
                 ts = torch.tensor([sec8], device=dev)
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
                 sec8 = float(ts.item())
+            # streaming: the same copies, but window i+1 is uploaded / computed while window i's results travel to the host
+            stream_n = args.steps + 2
+            for _ in tester.predict_stream([img_np] * 2):
+                pass
+            barrier()
+            t0 = time.perf_counter()
+            got = 0
+            for res in tester.predict_stream([img_np] * stream_n):
+                got += 1
+            torch.cuda.synchronize()
+            secs = (time.perf_counter() - t0) / stream_n
+            if world > 1:
+                ts = torch.tensor([secs], device=dev)
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                secs = float(ts.item())
+            e2e['streaming'] = {'value': units_per_step * world / secs, 'unit': unit_name, 'ms_per_step': secs * 1e3, 'windows': stream_n,
+                                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                                'api': 'Tester.predict_stream(iterable of numpy windows): same H2D / D2H per window, the device->host copies of '
+                                       'window i overlap window i+1 (2 device input buffers, 2 result slots)'}
             e2e['uint8_frames'] = {'value': units_per_step * world / sec8, 'unit': unit_name, 'h2d_bytes_per_step': int(h2d8),
                                    'd2h_bytes_per_step': int(d2h8), 'ms_per_step': sec8 * 1e3,
                                    'api': 'Tester.predict_frames(uint8 (B,T,%d,%d,3) video frames + bbox [cx,cy,scale]): process_image '

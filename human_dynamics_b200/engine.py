@@ -335,7 +335,7 @@ class HMMREngine(object):
 
     HOST_RING = 2            # result buffer sets handed out in turn: a returned dict stays valid for HOST_RING - 1 more calls
 
-    def predict_host(self, images_host, single_frame=False, fetch=None, bbox_params=None, on_main_ready=None):
+    def predict_host(self, images_host, single_frame=False, fetch=None, bbox_params=None, on_main_ready=None, defer=False):
         """The one host->device->host crossing of `sess.run(fetch_dict, feed_dict)` (tester.py:239-258).
 
         images_host: (B,T,S,S,3) float32 CPU tensor -- the crops `Tester.predict` is fed -- or, with `bbox_params` (B,T,3),
@@ -343,17 +343,27 @@ class HMMREngine(object):
         over PCIe, and no host-side resize).  Pinned (or cudaHostRegister-ed) memory gives real overlap: frames go up in
         H2D_PIECE pieces on a copy stream while the ResNet consumes earlier pieces; results come back into pinned host
         buffers owned by the engine (a ring of HOST_RING sets).  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes); the
-        copies are only complete after `torch.cuda.current_stream().synchronize()`."""
+        copies are only complete after `torch.cuda.current_stream().synchronize()`.
+
+        defer=True (streaming): returns (host, h2d, d2h, done_event) without making the current stream wait for the device->host
+        copies; the caller overlaps them with the NEXT window (device input buffers alternate, results land in the next ring
+        slot) and calls `done_event.synchronize()` before reading `host`.  See Tester.predict_stream."""
         u8 = bbox_params is not None
         if images_host.is_cuda or images_host.dim() != 5 or images_host.dtype != (torch.uint8 if u8 else torch.float32):
             raise _lib.HDError('predict_host: expected a CPU tensor (B,T,S,S,3) float32, or (B,T,H,W,3) uint8 with bbox_params')
         B, T = images_host.shape[0], images_host.shape[1]
         N = B * T
         flat = images_host.reshape((N,) + tuple(images_host.shape[2:]))
-        key = ('img', N, tuple(flat.shape[1:]), flat.dtype)
+        self._stream_step = getattr(self, '_stream_step', 0) + 1
+        ring = (self._stream_step & 1) if defer else 0          # streaming: the next window uploads while this one still computes
+        key = ('img', N, tuple(flat.shape[1:]), flat.dtype, ring)
         if key not in self._phi:
             self._phi[key] = torch.empty(tuple(flat.shape), dtype=flat.dtype, device=self.device)
-            self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._d2h_stream = torch.cuda.Stream(device=self.device)
+            self._img_read = {}                                  # device input buffer -> event: its last reader (the trunk) is done
+            self._d2h_done = None                                # event: the previous window's results have left the device
         if ('phi', N) not in self._phi:
             self._phi[('phi', N)] = torch.empty((N, self.resnet.out_dim), dtype=torch.float32, device=self.device)
         dev_img, phi = self._phi[key], self._phi[('phi', N)]
@@ -373,8 +383,11 @@ class HMMREngine(object):
             self._phi[ekey] = [torch.cuda.Event() for _ in starts]
         events = self._phi[ekey]
         main = torch.cuda.current_stream()
-        cs = self._copy_stream
-        cs.wait_stream(main)                         # the previous step may still read dev_img
+        cs, ds = self._copy_stream, self._d2h_stream
+        if defer and key in self._img_read:
+            cs.wait_event(self._img_read[key])       # only the window that last used THIS buffer has to be through its trunk
+        else:
+            cs.wait_stream(main)                     # the previous step may still read dev_img
         with torch.cuda.stream(cs):
             if u8:
                 geom_dev.copy_(self._phi[('geom', N)][0], non_blocking=True)
@@ -386,6 +399,11 @@ class HMMREngine(object):
             self._trunk(None, phi, events, frames=(dev_img, geom_dev))
         else:
             self._trunk(dev_img, phi, events)
+        ev_img = torch.cuda.Event()
+        ev_img.record(main)
+        self._img_read[key] = ev_img
+        if self._d2h_done is not None:               # the heads are about to overwrite the output buffers the previous window's
+            main.wait_event(self._d2h_done)          # device->host copies read (long finished by now: a formality, not a stall)
         want = list(fetch or self.FETCH_KEYS)
         host, counted = {}, [0]
         self._host_slot = (getattr(self, '_host_slot', -1) + 1) % self.HOST_RING
@@ -403,19 +421,28 @@ class HMMREngine(object):
                 host[k] = self._phi[hk]
                 counted[0] += v.numel() * 4
 
-        def main_ready(main_out):            # dt=0 outputs: device->host on the copy stream, overlapped with the delta heads
+        def main_ready(main_out):            # dt=0 outputs: device->host on their own stream, overlapped with the delta heads
             ev = torch.cuda.Event()
             ev.record(main)
-            cs.wait_event(ev)
-            to_host(main_out, cs)
+            ds.wait_event(ev)
+            to_host(main_out, ds)
             if on_main_ready is not None:    # (multi-GPU: the same moment starts the gather towards rank 0)
                 on_main_ready(main_out)
 
         out = self.predict_from_features(phi.view(B, T, -1), single_frame=single_frame, on_main_ready=main_ready)
-        to_host({k: v for k, v in out.items() if not k.startswith('_')}, main)
-        main.wait_stream(cs)                  # one synchronisation point for the caller: the current stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        ds.wait_event(ev)
+        to_host({k: v for k, v in out.items() if not k.startswith('_')}, ds)
+        done = torch.cuda.Event()
+        done.record(ds)
+        self._d2h_done = done
         d2h = counted[0]
-        return host, flat.numel() * flat.element_size() + (N * 16 if u8 else 0), d2h
+        h2d = flat.numel() * flat.element_size() + (N * 16 if u8 else 0)
+        if defer:
+            return host, h2d, d2h, done
+        main.wait_event(done)                 # one synchronisation point for the caller: the current stream
+        return host, h2d, d2h
 
     def predict_from_features(self, phi, single_frame=False, on_main_ready=None):
         B, T = phi.shape[0], phi.shape[1]

@@ -132,6 +132,29 @@ class Tester(object):
             return host
         return {k: (v.numpy().copy() if copy else v.numpy()) for k, v in host.items()}
 
+    def predict_stream(self, windows, bbox_params=None, copy=False):
+        """Streaming form of `predict` for a sequence of windows (what a video does): yields one result dict per window, in order.
+
+        windows: iterable of (B,T,S,S,3) float32 arrays -- or, with `bbox_params` (an iterable of (B,T,3) arrays alongside), of
+        (B,T,H,W,3) uint8 frame arrays.  Window i+1 is uploaded and computed while window i's 160 MB of results still travel
+        to the host (two device input buffers, two result slots), so the per-window cost is the GPU time, not GPU + PCIe tail.
+        A yielded dict is valid until the generator is advanced twice more (or pass copy=True)."""
+        boxes = iter(bbox_params) if bbox_params is not None else None
+        prev = None
+        for w in windows:
+            arr = self._as_pinned(np.ascontiguousarray(w)) if isinstance(w, np.ndarray) else w
+            bb = None
+            if boxes is not None:
+                bb = np.asarray(next(boxes), np.float64).reshape(self.batch_size, self.sequence_length, 3)
+            cur = self.engine.predict_host(arr, bbox_params=bb, defer=True)
+            if prev is not None:
+                prev[3].synchronize()
+                yield {k: (v.numpy().copy() if copy else v.numpy()) for k, v in prev[0].items()}
+            prev = cur
+        if prev is not None:
+            prev[3].synchronize()
+            yield {k: (v.numpy().copy() if copy else v.numpy()) for k, v in prev[0].items()}
+
     def predict_all_images(self, all_images, cache_features=True):
         """Sliding-window prediction over a whole sequence (tester.py:260-312).  all_images: N x H x W x 3.
 

@@ -270,3 +270,27 @@ def test_tester_host_paths_numpy_and_uint8_frames(weights, smpl_model):
     ref = nets_ref.hmmr_predict(ref_crops[None], weights, smpl_model)
     for k in ('omegas', 'verts', 'kps', 'verts_delta'):
         assert rel_err(got_u8[k][:1], ref[k]) < REL, (k, rel_err(got_u8[k][:1], ref[k]))
+
+
+def test_predict_stream_matches_predict(weights, smpl_model):
+    """Tester.predict_stream: windows pipelined two deep (upload / compute of window i+1 under the device->host copies of window i)
+    give exactly the per-window results of the synchronous predict, in order, for float crops and for uint8 frames."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from src.evaluation.tester import Tester
+    B, T, S = 2, 20, 64
+    tester = Tester(HMMRConfig(batch_size=B, sequence_length=T, img_size=S, weights=weights, smpl_model=smpl_model))
+    wins = [synthetic.make_images(B * T, seed=40 + i, size=S).reshape(B, T, S, S, 3) for i in range(4)]
+    want = [{k: v.copy() for k, v in tester.predict(w).items()} for w in wins]
+    got = [{k: v.copy() for k, v in r.items()} for r in tester.predict_stream(wins)]
+    assert len(got) == len(wins)
+    for g, w in zip(got, want):
+        for k in w:
+            assert np.array_equal(g[k], w[k]), k
+    rng = np.random.RandomState(0)
+    frames = [rng.randint(0, 256, size=(B, T, 96, 128, 3), dtype=np.uint8) for _ in range(3)]
+    boxes = [np.stack([rng.uniform(40, 90, B * T), rng.uniform(30, 70, B * T), rng.uniform(0.8, 1.3, B * T)], 1).reshape(B, T, 3) for _ in range(3)]
+    want8 = [{k: v.copy() for k, v in tester.predict_frames(f, b).items()} for f, b in zip(frames, boxes)]
+    got8 = [{k: v.copy() for k, v in r.items()} for r in tester.predict_stream(frames, bbox_params=boxes)]
+    for g, w in zip(got8, want8):
+        for k in ('omegas', 'verts', 'kps_delta'):
+            assert np.array_equal(g[k], w[k]), k
