@@ -157,7 +157,7 @@ __global__ void pack_conv1_planes_kernel(const float *__restrict__ img, uint2 *_
 
 // max_pool2d(1x1, stride s) = spatial subsampling: the identity shortcut of a strided bottleneck unit (A.4).  One float4 per thread.
 __global__ void subsample_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4, int Ho, int Wo, int s) {
-  // one warp per output pixel row segment: lanes stride over the pixel's channels, 4 independent 16-byte loads in flight per thread
+  // one warp per output pixel: lanes stride over the pixel's channels, up to 4 independent 16-byte loads in flight per thread
   const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= (long long)N * Ho * Wo) return;
   const int lane = threadIdx.x & 31;
@@ -174,6 +174,176 @@ __global__ void subsample_kernel(const float4 *__restrict__ in, float4 *__restri
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (c + 32 * u < C4) dst[c + 32 * u] = v[u];
+  }
+}
+
+// GroupNorm + ReLU + fp16 split in one pass (f_movie pre-activations, src/models.py:155-171,188-204): one warp per (clip, group).
+// Same statistics and the same affine as groupnorm_stats_kernel + the conv prologue it replaces (y = relu(x*gain + offset), gain =
+// rstd*gamma, offset = beta - mean*gain; identical summation order), but the result leaves as the pre-split A operand of the
+// tensor-core conv, so the temporal convs take the cp.async producer instead of the register-staged one.  T*cg <= 40*32 elements.
+__global__ void __launch_bounds__(128) groupnorm_relu_split_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                                   const float *__restrict__ beta, __half *__restrict__ out_hi,
+                                                                   __half *__restrict__ out_lo, int B, int T, int C, int groups, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wg >= B * groups) return;
+  const int b = wg / groups, g = wg % groups;
+  const int cg = C / groups;
+  const size_t base = (size_t)b * T * C + (size_t)g * cg;
+  const int cnt = T * cg;
+  constexpr int MAXE = 40;
+  float v[MAXE];
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    // element i of the group = (row i / cg, channel i % cg); cg == 64 (f_movie: 2048 / 32) makes that (e >> 1, lane + 32 (e & 1))
+    const size_t off = cg == 64 ? (size_t)(e >> 1) * C + (lane + 32 * (e & 1)) : (size_t)(i / cg) * C + (i % cg);
+    v[e] = i < cnt ? __ldg(x + base + off) : 0.f;
+    if (i < cnt) s += v[e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)cnt;
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    if (i < cnt) { const float d = v[e] - mean; q += d * d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)cnt + eps);
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int i = lane + 32 * e;
+    if (i >= cnt) continue;
+    const int cin = cg == 64 ? lane + 32 * (e & 1) : i % cg;
+    const int ch = g * cg + cin;
+    const float gn = rstd * __ldg(gamma + ch);
+    const float off = __ldg(beta + ch) - mean * gn;
+    const float y = fmaxf(v[e] * gn + off, 0.f);
+    uint32_t h, l;
+    hd::split_f16x2(y, 0.f, h, l);
+    const size_t o = base + (cg == 64 ? (size_t)(e >> 1) * C : (size_t)(i / cg) * C) + cin;
+    out_hi[o] = __ushort_as_half((unsigned short)(h & 0xffffu));
+    out_lo[o] = __ushort_as_half((unsigned short)(l & 0xffffu));
+  }
+}
+
+// fp32 -> fp16 head / remainder pair (the A operand format of the tensor-core GEMM), 4 elements per thread.
+__global__ void split_f16_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(x + i);
+  uint32_t h0, l0, h1, l1;
+  hd::split_f16x2(v.x, v.y, h0, l0);
+  hd::split_f16x2(v.z, v.w, h1, l1);
+  hi[i] = make_uint2(h0, h1);
+  lo[i] = make_uint2(l0, l1);
+}
+
+// IEF fc1, theta part (src/models.py:402,102: state = concat[phi, theta] -> fc1): h1 = relu(P + theta . W1[2048:]) with P = phi . W1[:2048]
+// + b1 hoisted out of the stage loop.  K = 85 / 72 is far too short for the tensor-core tile; here a block takes 8 rows and all C
+// columns (thread = 4 columns), theta rows sit in smem, W streams from L2 (348 KB, read once per block).  Output = the pre-split
+// fp16 pair fc2's cp.async producer loads (and optionally fp32).
+__global__ void __launch_bounds__(256) ief_fc1_theta_kernel(const float *__restrict__ P, const float *__restrict__ theta, int theta_ld,
+                                                            const float *__restrict__ W, int K, int Cc, __half *__restrict__ out_hi,
+                                                            __half *__restrict__ out_lo, float *__restrict__ out_f32, int N) {
+  __shared__ float th[8][96];
+  const int r0 = blockIdx.x * 8;
+  for (int i = threadIdx.x; i < 8 * 96; i += 256) {
+    const int r = i / 96, k = i - r * 96;
+    th[r][k] = (r0 + r < N && k < K) ? __ldg(theta + (size_t)(r0 + r) * theta_ld + k) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 4; c < Cc; c += 1024) {
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    for (int k0 = 0; k0 < K; k0 += 8) {          // 8 weight rows in flight: the loop is L2-latency-, not FMA-bound otherwise
+      float4 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        w[u] = (k0 + u < K) ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)(k0 + u) * Cc + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float t = th[r][k0 + u];           // zero beyond K (th is 96 wide, K <= 96)
+          acc[r][0] += t * w[u].x; acc[r][1] += t * w[u].y; acc[r][2] += t * w[u].z; acc[r][3] += t * w[u].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r0 + r >= N) break;
+      const size_t o = (size_t)(r0 + r) * Cc + c;
+      const float4 p = __ldg(reinterpret_cast<const float4 *>(P + o));
+      const float y0 = fmaxf(acc[r][0] + p.x, 0.f), y1 = fmaxf(acc[r][1] + p.y, 0.f), y2 = fmaxf(acc[r][2] + p.z, 0.f),
+                  y3 = fmaxf(acc[r][3] + p.w, 0.f);
+      if (out_f32) *reinterpret_cast<float4 *>(out_f32 + o) = make_float4(y0, y1, y2, y3);
+      if (out_hi) {
+        uint32_t h0, l0, h1, l1;
+        hd::split_f16x2(y0, y1, h0, l0);
+        hd::split_f16x2(y2, y3, h1, l1);
+        *reinterpret_cast<uint2 *>(out_hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2 *>(out_lo + o) = make_uint2(l0, l1);
+      }
+    }
+  }
+}
+
+// IEF fc3 + update (models.py:113,410): theta_out = theta_prev + h2 . W3 + b3, W3 [K, D] with D = 85 / 72: one tensor-core tile
+// would serialise K = 1024 on 5 CTAs.  Block = 8 rows x 8 warps; warp w sums k in [w*K/8, (w+1)*K/8) for the block's rows (lane = output
+// column, 3 per lane), partial sums meet in smem in warp order: fixed summation order, bit-reproducible.
+__global__ void __launch_bounds__(256) ief_fc3_kernel(const float *__restrict__ h2, const float *__restrict__ W, const float *__restrict__ bias,
+                                                      const float *__restrict__ prev, int prev_ld, float *__restrict__ out, int out_ld, int N,
+                                                      int K, int D) {
+  extern __shared__ float sm[];
+  float *hs = sm;                         // [8][K]
+  float *part = sm + 8 * K;               // [8 warps][8 rows][96]
+  const int r0 = blockIdx.x * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    hs[i] = (r0 + r < N) ? __ldg(h2 + (size_t)(r0 + r) * K + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[8][3];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.f;
+  const int kper = K / 8;
+  const bool c1 = lane + 32 < D, c2 = lane + 64 < D;
+  for (int k0 = warp * kper; k0 < (warp + 1) * kper; k0 += 8) {       // (kper % 8 == 0 is required by the host entry)
+    float w0[8], w1[8], w2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float *wr = W + (size_t)(k0 + u) * D;
+      w0[u] = __ldg(wr + lane); w1[u] = c1 ? __ldg(wr + lane + 32) : 0.f; w2[u] = c2 ? __ldg(wr + lane + 64) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float h = hs[r * K + k0 + u];
+        acc[r][0] += h * w0[u]; acc[r][1] += h * w1[u]; acc[r][2] += h * w2[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float *pp = part + (warp * 8 + r) * 96;
+    pp[lane] = acc[r][0]; pp[lane + 32] = acc[r][1]; pp[lane + 64] = acc[r][2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * D; i += 256) {
+    const int r = i / D, j = i - r * D;
+    if (r0 + r >= N) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[(w * 8 + r) * 96 + j];
+    out[(size_t)(r0 + r) * out_ld + j] = (s + __ldg(bias + j)) + prev[(size_t)(r0 + r) * prev_ld + j];
   }
 }
 
