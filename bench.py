@@ -241,7 +241,14 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        v, sec, cores, sample, procs = cpu_reference_run_multi(args.workload, args.steps, args.warmup)
+        # the port stops scaling past ~32 threads, and several 32-thread processes fight over memory bandwidth (measured on this
+        # pool's 128-core hosts: 4 x 32 threads = 17.6 frames/s in total vs 23.4 for one process): time both, report the better
+        v1, sec1, cores1, sample1 = cpu_reference_run(args.workload, args.steps, args.warmup)
+        vm, secm, coresm, samplem, procs = cpu_reference_run_multi(args.workload, args.steps, args.warmup)
+        if procs > 1 and vm > v1:
+            v, sec, cores, sample = vm, secm, coresm, samplem + ' [one 32-thread process: %.1f %s]' % (v1, unit_name)
+        else:
+            v, sec, cores, sample = v1, sec1, cores1, sample1 + (' [%d processes x 32 threads together: %.1f %s]' % (procs, vm, unit_name) if procs > 1 else '')
         line = {'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit_name, 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
