@@ -312,7 +312,10 @@ def main():
                 # while the delta heads still compute; the delta-independent keys need nothing else
                 def main_ready(o):
                     gatherer.start({k: o[k] for k in gather_keys if k in o})
-                out = eng.predict(img_dev, single_frame=single, on_main_ready=main_ready)
+                if args.graph and not single:       # two graph launches per step, the gather starts between them
+                    out, last['nodes'] = eng.predict_graphed_split(img_dev, main_ready)
+                else:
+                    out = eng.predict(img_dev, single_frame=single, on_main_ready=main_ready)
                 rest = {k: out[k] for k in gather_keys if k.endswith('_delta')}
                 if rest:
                     gatherer.start(rest)
@@ -503,7 +506,7 @@ def main():
                 'clocks': clocks, 'gpu_launches': launches,
                 'gpu_launches_per_step': launches / max(1, args.steps)}
         if graph_nodes:
-            line['cuda_graph'] = {'graph_launches_per_step': 1, 'kernel_nodes_per_graph': graph_nodes}
+            line['cuda_graph'] = {'graph_launches_per_step': 1 if world == 1 else 2, 'kernel_nodes_per_step': graph_nodes}
         if e2e:
             line['e2e'] = e2e
         if roofline:

@@ -331,6 +331,42 @@ class HMMREngine(object):
         ent[0].replay()
         return ent[1], ent[2]
 
+    def predict_graphed_split(self, images, on_main_ready):
+        """`predict_graphed` in two graphs with a host hook between them: graph A ends when the dt=0 outputs are complete (trunk,
+        f_movie, main IEF head, SMPL), `on_main_ready(out)` runs (multi-GPU: starts their gather to rank 0 on a side stream),
+        graph B is the delta heads.  Two graph launches per window instead of ~200 kernel launches, and the gather still overlaps
+        the delta heads.  Returns (out, kernel_nodes)."""
+        key = (images.data_ptr(), tuple(images.shape), 'split')
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            self.predict(images)                                       # eager warm-up
+            torch.cuda.synchronize()
+            n0 = int(_lib.lib.hd_launch_count())
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            box = {}
+            with torch.cuda.stream(side):
+                ga.capture_begin()
+
+                def boundary(out_main):
+                    ga.capture_end()
+                    box['main'] = dict(out_main)
+                    gb.capture_begin()
+                out = self.predict(images, on_main_ready=boundary)
+                gb.capture_end()
+            torch.cuda.current_stream().wait_stream(side)
+            keep = [dict(c) for c in (self._resnet_plans, self._fmovie_plans, self._ief_plans, self._hal_plans, self._theta0,
+                                      self._phi, self._outs)] + [dict(self.smpl._tc_bufs)]
+            ent = (ga, gb, out, box['main'], int(_lib.lib.hd_launch_count()) - n0, images, keep)
+            self._graphs[key] = ent
+        ent[0].replay()
+        on_main_ready(ent[3])
+        ent[1].replay()
+        return ent[2], ent[4]
+
     FETCH_KEYS = tuple(a + b for b in ('', '_delta') for a in ('cams', 'joints', 'kps', 'poses', 'shapes', 'verts', 'omegas'))
 
     HOST_RING = 2            # result buffer sets handed out in turn: a returned dict stays valid for HOST_RING - 1 more calls

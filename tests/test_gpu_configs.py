@@ -294,3 +294,21 @@ def test_predict_stream_matches_predict(weights, smpl_model):
     for g, w in zip(got8, want8):
         for k in ('omegas', 'verts', 'kps_delta'):
             assert np.array_equal(g[k], w[k]), k
+
+
+def test_split_graph_replay_equals_eager(weights, smpl_model):
+    """predict_graphed_split: graph A (up to the dt=0 outputs), host hook, graph B (delta heads) == eager predict, hook sees dt=0."""
+    from human_dynamics_b200 import synthetic, HMMRConfig
+    from human_dynamics_b200.engine import HMMREngine
+    B, T, S = 2, 20, 64
+    eng = HMMREngine(weights, smpl_model, HMMRConfig(batch_size=B, sequence_length=T, img_size=S))
+    a = torch.from_numpy(synthetic.make_images(B * T, seed=5, size=S)).cuda().view(B, T, S, S, 3)
+    eager = {k: v.clone() for k, v in eng.predict(a).items() if not k.startswith('_')}
+    seen = []
+    buf = a.clone()
+    for _ in range(2):
+        out, nodes = eng.predict_graphed_split(buf, lambda o: seen.append(sorted(o.keys())))
+    torch.cuda.synchronize()
+    assert nodes > 100 and len(seen) == 3 and 'verts' in seen[-1] and 'verts_delta' not in seen[-1]      # (capture + 2 replays)
+    for k in eager:
+        assert torch.equal(out[k], eager[k]), k
