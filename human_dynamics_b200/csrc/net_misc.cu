@@ -29,7 +29,7 @@ __global__ void maxpool3x3s2_kernel(const float4 *__restrict__ in, float4 *__res
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  out[i] = m;
+  if (out) out[i] = m;
   if (out_hi) {        // relu(bn(x)) of the first bottleneck unit, as an fp16 head/remainder pair
     const float4 sc = __ldg(scale + c), sh = __ldg(shift + c);
     const float y[4] = {fmaxf(m.x * sc.x + sh.x, 0.f), fmaxf(m.y * sc.y + sh.y, 0.f), fmaxf(m.z * sc.z + sh.z, 0.f),
@@ -373,7 +373,7 @@ int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *ou
 
 int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, const float *scale, const float *shift,
                          void *out_hi, void *out_lo, void *stream) {
-  HD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hd_maxpool3x3s2_same: bad arguments");
+  HD_REQUIRE(in && (out || out_hi) && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hd_maxpool3x3s2_same: bad arguments");
   HD_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && (!out_hi || (scale && shift)), "hd_maxpool3x3s2_same: split output needs scale, shift, out_hi and out_lo");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int pth = (Ho - 1) * 2 + 3 - H, ptw = (Wo - 1) * 2 + 3 - W;

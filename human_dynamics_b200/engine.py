@@ -140,7 +140,7 @@ class HMMREngine(object):
             if stage == 'A':
                 nxt = self.resnet.units[cut]['pre'] if cut < nu else None
                 self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(0, cut), root=True, tail=False,
-                                                     next_pre=nxt)
+                                                     next_pre=nxt, next_has_shortcut=cut < nu and 'shortcut' in self.resnet.units[cut])
             else:
                 self._resnet_plans[key] = ResNetPlan(self.resnet, n, size, self.impl, units=(cut, nu), root=False, tail=True)
         return self._resnet_plans[key]

@@ -256,6 +256,7 @@ class ConvOp(object):
             check(rc, 'hd_conv_gemm')
 
 
+DROP_DEAD_FP32 = os.environ.get('HD_DROP_DEAD_FP32', '1') != '0'   # A/B switch: skip fp32 block outputs nobody reads
 FAST_HEADS = os.environ.get('HD_FAST_HEADS', '1') != '0'          # A/B switch: f_movie / IEF through the pre-split + small-GEMM kernels
 CONV1_PLANES = os.environ.get('HD_CONV1_PLANES', '1') != '0'      # A/B switch: conv1 from padded fp16 planes vs fp32 row-segment gather
 
@@ -360,7 +361,8 @@ class ResNetPlan(object):
     root=True prepends conv1 + pool1; tail=True appends postnorm + global mean.
     """
 
-    def __init__(self, packed: PackedResNet, n, size=224, impl='auto', units=None, root=True, tail=True, next_pre=None):
+    def __init__(self, packed: PackedResNet, n, size=224, impl='auto', units=None, root=True, tail=True, next_pre=None,
+                 next_has_shortcut=False):
         self.p = packed
         self.n = n
         self.size = size
@@ -405,6 +407,7 @@ class ResNetPlan(object):
             self.conv1_op = packed.conv1.bind(self.bufS, n, size, size, self.bufS, in_ld=3, impl=impl)   # `in_` is set per run
         self.in_refs = []                     # (op, field) descriptor fields that read the stage input
         self.pool_split = None
+        self.pool_f32_dead = False
         x, y = self.bufA, self.bufB
         units = packed.units[lo:hi]
         if self.split:
@@ -415,6 +418,7 @@ class ResNetPlan(object):
             self.in_split = xs
             if root:
                 self.pool_split = (units[0]['pre'][0], units[0]['pre'][1], xs)
+                self.pool_f32_dead = DROP_DEAD_FP32 and 'shortcut' in units[0]
             self.out_split = None
             for ui, unit in enumerate(units):
                 s = unit['stride']
@@ -439,7 +443,11 @@ class ResNetPlan(object):
                 last = ui == len(units) - 1
                 nxt = units[ui + 1]['pre'] if not last else next_pre        # the next unit's pre-activation BN (+ReLU)
                 osplit = ys if nxt is not None else None
-                self.ops.append(unit['conv3'].bind(None, n, Ho, Ho, y, inp_split=r2, res=res, res_geom=res_geom, impl=impl,
+                # the fp32 block output only feeds an IDENTITY shortcut: when the next unit changes depth (first unit of a block) its
+                # shortcut is a conv of the pre-activation, and the fp32 copy would be written for nobody
+                nxt_conv_shortcut = ('shortcut' in units[ui + 1]) if not last else bool(next_has_shortcut)
+                y_out = None if (osplit is not None and nxt_conv_shortcut and DROP_DEAD_FP32) else y
+                self.ops.append(unit['conv3'].bind(None, n, Ho, Ho, y_out, inp_split=r2, res=res, res_geom=res_geom, impl=impl,
                                                    out_split=osplit, post2=(nxt[0], nxt[1], 1) if nxt is not None else None))
                 if ui == 0 and 'shortcut' not in unit and not (s > 1 and SUBSAMPLE_RES):
                     self.in_refs.append((self.ops[-1], 'res', 2))
@@ -494,7 +502,8 @@ class ResNetPlan(object):
         """Let the last unit write its output feature map [n, out_hw, out_hw, out_depth] straight into `t` (and, in split
         mode, the next stage's pre-activated pair into `t_split`)."""
         op = self.ops[-1]
-        op.rebind('out', t)
+        if op.d.out:                          # (no fp32 output when the consumer's shortcut is a conv)
+            op.rebind('out', t)
         if t_split is not None:
             op.rebind('out_hi', t_split[0])
             op.rebind('out_lo', t_split[1])
@@ -520,7 +529,7 @@ class ResNetPlan(object):
                 check(lib.hd_conv1_7x7s2(fptr(images), fptr(p.conv1_w), fptr(p.conv1_b), fptr(self.bufS), n, self.size, self.size, st),
                       'hd_conv1_7x7s2')
             ps = self.pool_split
-            check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), fptr(self.bufA), n, self.H1, self.H1, 64,
+            check(lib.hd_maxpool3x3s2_same(fptr(self.bufS), None if self.pool_f32_dead else fptr(self.bufA), n, self.H1, self.H1, 64,
                                            fptr(ps[0]) if ps else None, fptr(ps[1]) if ps else None,
                                            C.c_void_p(ps[2][0].data_ptr()) if ps else None,
                                            C.c_void_p(ps[2][1].data_ptr()) if ps else None, st), 'hd_maxpool3x3s2_same')

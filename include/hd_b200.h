@@ -120,7 +120,8 @@ int hd_pack_conv1_planes(const float *img, void *plane_hi, void *plane_lo, int N
 int hd_conv1_7x7s2(const float *in, const float *w, const float *bias, float *out, int N, int H, int W, void *stream);
 /* pool1: 3x3 stride 2 max pool, TF SAME padding (pad 0 top/left, 1 bottom/right for even sizes).
  * Optional second output (out_hi/out_lo non-NULL): relu(v*scale[c] + shift[c]) as an fp16 head/remainder pair
- * (the first bottleneck unit's pre-activation, pre-split for the tensor-core kernel). */
+ * (the first bottleneck unit's pre-activation, pre-split for the tensor-core kernel); `out` may then be NULL (the first unit's
+ * shortcut is a conv of the pre-activation, so nobody reads the fp32 pool output). */
 int hd_maxpool3x3s2_same(const float *in, float *out, int N, int H, int W, int C, const float *scale, const float *shift,
                          void *out_hi, void *out_lo, void *stream);
 /* slim's identity shortcut of a strided unit: max_pool2d(x, [1,1], stride) = x[:, ::s, ::s, :] (A.4).  in [N,H,W,C] -> out

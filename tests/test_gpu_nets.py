@@ -124,6 +124,7 @@ def test_conv_gemm_tcgen05_3xf16(case):
     (7, 28, 64, 256, 1, 1, True, True),      # K=64: 43 M-tiles x 2 N-tiles on 148 CTAs, ragged last tile (5488 rows)
     (640, 7, 256, 64, 1, 1, False, False),   # BN=64 tile, 245 tiles > 148 CTAs: several tiles per CTA through the staging ring
     (9, 14, 128, 512, 1, 1, True, False),    # residual + split output only (no fp32 store)
+    (4, 14, 256, 1024, 1, 1, True, False),   # same at K = 256 (last unit of block3: the next unit's shortcut is a conv)
     (9, 14, 256, 1024, 1, 1, False, True),   # no residual, both outputs
     (300, 14, 64, 256, 1, 1, True, True),    # 460 M-tiles x 2: every CTA walks ~6 tiles (ring wrap-around, barrier phases)
     (5, 14, 128, 96, 1, 1, True, True),      # Cout = 96: one 128-wide N tile whose last 32-column slab lies outside the tensor
@@ -191,6 +192,26 @@ def test_resnet_matches_oracle(weights, impl, n, size):
     ref64 = nets_ref.encoder_resnet(img, weights, torch.float64).numpy()
     assert rel_err(ref, ref64) < 1e-5
     assert rel_err(phi.cpu().numpy(), ref) < REL
+
+
+def test_resnet_dead_fp32_outputs_are_dead(weights, monkeypatch):
+    """Skipping the fp32 copies nobody reads (pool1 output, block outputs in front of a conv shortcut) must not change a bit."""
+    from human_dynamics_b200 import synthetic, nets
+    from human_dynamics_b200.nets import PackedResNet, ResNetPlan
+    dev = torch.device('cuda')
+    img = torch.from_numpy(synthetic.make_images(3, seed=5, size=224)).to(dev)
+    packed = PackedResNet(weights, dev, tc='auto')
+    outs = []
+    for drop in (True, False):
+        monkeypatch.setattr(nets, 'DROP_DEAD_FP32', drop)
+        plan = ResNetPlan(packed, 3, 224, 'auto')
+        assert plan.split and plan.pool_f32_dead == drop
+        assert sum(1 for op in plan.ops if getattr(op, 'd', None) is not None and not op.d.out and op.d.res) == (3 if drop else 0)
+        phi = torch.empty((3, 2048), dtype=torch.float32, device=dev)
+        plan.run(img, phi)
+        torch.cuda.synchronize()
+        outs.append(phi.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize('impl', ['simt', 'auto'])
