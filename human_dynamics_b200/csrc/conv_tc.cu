@@ -721,7 +721,10 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       }
     } else if (warp == W_MMA) {
       // =============================== MMA issuer ===============================
-      if (lane == 0) {
+      // The whole warp walks the loop in lock step (all lanes poll the barriers, all values are warp-uniform) and ONE elected lane issues
+      // the MMAs and commits of a chunk: under a divergent `lane == 0` the compiler wraps every tcgen05 instruction in an
+      // ELECT / BRA.U.ANY loop (~55 issue cycles per 64-cycle MMA, measured: the issue loop, not the tensor pipe, paced the kernel).
+      {
         const bool prof = p.dbg != nullptr && blockIdx.x == 0;
         long long t_wfull = 0, t_wacc = 0, t_start = prof ? clock64() : 0;
         int q = 0;
@@ -752,6 +755,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
             const uint64_t da_hi = make_smem_desc(a_hi), da_lo = make_smem_desc(a_lo);
             const uint64_t db_hi = make_smem_desc(b_hi), db_lo = make_smem_desc(b_lo);
+            if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                // UMMA K = 8 tf32 / 16 fp16 = 32 bytes: advance inside the swizzle atom
               const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -769,9 +773,11 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
             }
             umma_commit(empty_bar(s));                   // frees the stage once these MMAs have read it
             if ((kc % PCH) == PCH - 1 || kc == num_k - 1) umma_commit(accf_bar(b));     // hand accumulator b to the drain warps
+            }
+            __syncwarp();
           }
         }
-        if (prof) { p.dbg[5] = clock64() - t_start; p.dbg[6] = t_wfull; p.dbg[7] = t_wacc; }
+        if (prof && lane == 0) { p.dbg[5] = clock64() - t_start; p.dbg[6] = t_wfull; p.dbg[7] = t_wacc; }
       }
     }
   }

@@ -140,8 +140,8 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
     cp_async_commit();
     cp_async_wait<0>();
   } else if (warp == W_MMA) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (whole warp in lock step, one elected lane issues: see conv_tc.cu) ==========
+    {
       uint32_t w_phase = 0;
       int q = 0;
       for (WorkIter wi(N, V, blockIdx.x); wi.valid(); wi.next(gridDim.x), ++q) {
@@ -159,15 +159,18 @@ smpl_lbs_tc_kernel(const __half *__restrict__ w_hi, const __half *__restrict__ w
         const uint32_t w_s = smem_base + OFF_W + s * 2 * W_TILE;
         const uint64_t da_hi = make_smem_desc(w_s), da_lo = make_smem_desc(w_s + W_TILE);
         const uint64_t db_hi = make_smem_desc(smem_base + OFF_B), db_lo = make_smem_desc(smem_base + OFF_B + B_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {                               // K = 32 fp16 = two UMMA K steps of 32 bytes
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          umma_f16(acc, da_hi + adv, db_hi + adv, LBS_IDESC, k != 0);
-          umma_f16(acc, da_lo + adv, db_hi + adv, LBS_IDESC, 1u);
-          umma_f16(acc, da_hi + adv, db_lo + adv, LBS_IDESC, 1u);
+          for (int k = 0; k < 2; ++k) {                             // K = 32 fp16 = two UMMA K steps of 32 bytes
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma_f16(acc, da_hi + adv, db_hi + adv, LBS_IDESC, k != 0);
+            umma_f16(acc, da_lo + adv, db_hi + adv, LBS_IDESC, 1u);
+            umma_f16(acc, da_hi + adv, db_lo + adv, LBS_IDESC, 1u);
+          }
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(s));
         }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(s));
+        __syncwarp();
       }
     }
   } else {

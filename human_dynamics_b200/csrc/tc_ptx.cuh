@@ -48,6 +48,13 @@ static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bu
 template <int N>
 static __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 static __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// One lane of a CONVERGED warp (elect.sync).  Code guarded by this predicate is known to the compiler to run in a single thread, so
+// warp-uniform instructions (tcgen05.mma / commit, TMA) are emitted once, not inside a per-active-lane ELECT loop as under `lane == 0`.
+static __device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 static __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
