@@ -188,6 +188,66 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
       // ---- pre-split fp16 activations: cp.async straight into the swizzled tile, STAGES chunks in flight, no registers ----
       const __half *ihi = reinterpret_cast<const __half *>(p.in_hi);
       const __half *ilo = reinterpret_cast<const __half *>(p.in_lo);
+      if (!p.planes && p.KH * p.KW <= 32 && (long long)p.n_img * p.H * p.W * p.in_ld < (1ll << 31)) {
+        // Lean loop (these warps run on 32 registers and, on the long-K layers, pace the whole kernel: the general loop below spent
+        // ~280 instructions per chunk on two integer divisions, 64-bit addressing and spilled row state).  Per tile: one 32-bit
+        // element offset and one tap-validity bit mask per row.  Per chunk: (tap, channel) advance incrementally -- a 64-wide chunk
+        // lies inside one tap because Cin % 64 == 0 -- and a row costs a shift, an add and two cp.asyncs.  Taken when the input's
+        // element offsets fit 32 bits and the kernel window fits the 32-bit tap mask; anything else runs the general loop.
+        const uint32_t off0 = (uint32_t)rb * 128u + sw_off;       // row rb + 32 i of the tile: + i * 4096
+        int base[4];
+        uint32_t mask[4];
+        int kc = 0, ti = 0, tap = 0, ci0 = 0, kx = 0, ky = 0, tap_off = 0;
+        for (int q = 0; q < total; ++q) {
+          if (kc == 0) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m0 = (tile / tiles_n) * BM + rb;
+            const int hw = p.Ho * p.Wo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + 32 * i;
+              uint32_t mk = 0;
+              int b = 0;
+              if (m < p.M) {
+                const int n = m / hw;
+                const int r = m - n * hw;
+                const int oy = r / p.Wo, ox = r - oy * p.Wo;
+                const int iy0 = oy * p.stride - p.pad_t, ix0 = ox * p.stride - p.pad_l;
+                b = ((n * p.H + iy0) * p.W + ix0) * p.in_ld + j * 8;
+                int t = 0;
+                for (int yy = 0; yy < p.KH; ++yy)
+                  for (int xx = 0; xx < p.KW; ++xx, ++t)
+                    if ((unsigned)(iy0 + yy) < (unsigned)p.H && (unsigned)(ix0 + xx) < (unsigned)p.W) mk |= 1u << t;
+              }
+              base[i] = b;
+              mask[i] = mk;
+            }
+            tap = 0; ci0 = 0; kx = 0; ky = 0; tap_off = 0;
+          }
+          const int s = q % STAGES;
+          const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+          long long tw0 = prof ? clock64() : 0;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (prof) t_wait += clock64() - tw0;
+          const uint32_t a_hi = smem_base + s * C::STAGE_BYTES + off0;
+          const int eo = tap_off + ci0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = (mask[i] >> tap) & 1u;
+            const int e = ok ? base[i] + eo : 0;
+            cp_async16(a_hi + i * 4096, ihi + e, ok ? 16u : 0u);
+            cp_async16(a_hi + A_TILE_BYTES + i * 4096, ilo + e, ok ? 16u : 0u);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          ci0 += BKE;
+          if (ci0 == p.Cin) {
+            ci0 = 0; ++tap;
+            if (++kx == p.KW) { kx = 0; ++ky; }
+            tap_off = (ky * p.W + kx) * p.in_ld;
+          }
+          if (++kc == num_k) { kc = 0; ++ti; }
+        }
+      } else {
       RowState rs;
       int kc = 0, ti = 0;
       for (int q = 0; q < total; ++q) {
@@ -225,6 +285,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         // chunks are genuinely in flight.  The MMA thread issues the generic->async proxy fence after its wait.
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
         if (++kc == num_k) { kc = 0; ++ti; }
+      }
       }
       cp_async_commit();
       cp_async_wait<0>();
