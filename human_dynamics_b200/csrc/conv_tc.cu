@@ -247,6 +247,52 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           }
           if (++kc == num_k) { kc = 0; ++ti; }
         }
+      } else if (p.planes && (long long)p.n_img * p.H * p.W * p.in_ld < (1ll << 31)) {
+        // resnet conv1 over the padded RGBX fp16 planes, same lean scheme: Cin = 32 halves = one kernel row of 7(+1) pixels x 4, so a
+        // 64-wide chunk holds TWO kernel rows (taps 2 kc and 2 kc + 1); this thread's 16-byte piece is pixels 2*(j&3), 2*(j&3)+1 of row
+        // 2 kc + (j >> 2).  KH = 8: row 7 is a phantom (zero weights) and is zero-filled.  No padding tests: the planes are pre-padded.
+        const uint32_t off0 = (uint32_t)rb * 128u + sw_off;
+        const int jt = j >> 2;
+        const int row_step = 2 * p.W * (int)p.in_ld;                // two kernel rows per chunk
+        int base[4];
+        int kc = 0, ti = 0;
+        for (int q = 0; q < total; ++q) {
+          if (kc == 0) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m0 = (tile / tiles_n) * BM + rb;
+            const int hw = p.Ho * p.Wo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + 32 * i;
+              int b = -1;
+              if (m < p.M) {
+                const int n = m / hw;
+                const int r = m - n * hw;
+                const int oy = r / p.Wo, ox = r - oy * p.Wo;
+                b = ((n * p.H + oy * p.stride + jt) * p.W + ox * p.stride) * (int)p.in_ld + (j & 3) * 8;
+              }
+              base[i] = b;
+            }
+          }
+          const int s = q % STAGES;
+          const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+          long long tw0 = prof ? clock64() : 0;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (prof) t_wait += clock64() - tw0;
+          const uint32_t a_hi = smem_base + s * C::STAGE_BYTES + off0;
+          const bool tap_ok = 2 * kc + jt < 7;
+          const int eo = kc * row_step;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = tap_ok && base[i] >= 0;
+            const int e = ok ? base[i] + eo : 0;
+            // neighbouring output pixels read overlapping 64-byte windows (each 16-byte piece 4x): keep them in L1
+            cp_async16_ca(a_hi + i * 4096, ihi + e, ok ? 16u : 0u);
+            cp_async16_ca(a_hi + A_TILE_BYTES + i * 4096, ilo + e, ok ? 16u : 0u);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          if (++kc == num_k) { kc = 0; ++ti; }
+        }
       } else {
       RowState rs;
       int kc = 0, ti = 0;

@@ -155,25 +155,34 @@ __global__ void pack_conv1_planes_kernel(const float *__restrict__ img, uint2 *_
   lo[o] = make_uint2(l0, l1);
 }
 
-// max_pool2d(1x1, stride s) = spatial subsampling: the identity shortcut of a strided bottleneck unit (A.4).  One float4 per thread.
-__global__ void subsample_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4, int Ho, int Wo, int s) {
-  // one warp per output pixel: lanes stride over the pixel's channels, up to 4 independent 16-byte loads in flight per thread
-  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= (long long)N * Ho * Wo) return;
+// max_pool2d(1x1, stride s) = spatial subsampling: the identity shortcut of a strided bottleneck unit (A.4).
+// One warp per 4 consecutive output pixels: lanes stride over the channels, the 4 pixels' loads are independent, so a thread has
+// 4 (C = 128) to 8 (C >= 256, loop unrolled twice) 16-byte loads in flight -- the kernel is a pure strided copy and lives on that.
+__global__ void __launch_bounds__(256) subsample_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int N, int H, int W, int C4,
+                                                        int Ho, int Wo, int s) {
+  constexpr int PPW = 4;
+  const long long total = (long long)N * Ho * Wo;
+  const long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW;
+  if (pix0 >= total) return;
   const int lane = threadIdx.x & 31;
-  const int ox = (int)(pix % Wo);
-  const int oy = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  const float4 *src = in + ((size_t)((size_t)n * H + (size_t)oy * s) * W + (size_t)ox * s) * C4;
-  float4 *dst = out + (size_t)pix * C4;
-  for (int c = lane; c < C4; c += 128) {
-    float4 v[4];
+  const float4 *src[PPW];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c + 32 * u < C4) v[u] = __ldg(src + c + 32 * u);
+  for (int u = 0; u < PPW; ++u) {
+    const long long pix = pix0 + u < total ? pix0 + u : total - 1;      // tail: duplicates of the last pixel, never stored
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    src[u] = in + ((size_t)((size_t)n * H + (size_t)oy * s) * W + (size_t)ox * s) * C4;
+  }
+  float4 *dst = out + (size_t)pix0 * C4;
+#pragma unroll 2
+  for (int c = lane; c < C4; c += 32) {
+    float4 v[PPW];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c + 32 * u < C4) dst[c + 32 * u] = v[u];
+    for (int u = 0; u < PPW; ++u) v[u] = __ldg(src[u] + c);
+#pragma unroll
+    for (int u = 0; u < PPW; ++u)
+      if (pix0 + u < total) dst[(size_t)u * C4 + c] = v[u];
   }
 }
 
@@ -435,8 +444,8 @@ extern "C" int hd_subsample(const float *in, float *out, int N, int H, int W, in
   HD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && stride >= 1 && hd::aligned16(in) && hd::aligned16(out),
              "hd_subsample: bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const long long total = (long long)N * Ho * Wo;            // one warp per output pixel
-  subsample_kernel<<<hd::ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N,
+  const long long total = (long long)N * Ho * Wo;            // one warp per 4 output pixels, 8 warps per block
+  subsample_kernel<<<hd::ceil_div(total, 32), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(out), N,
                                                                              H, W, C / 4, Ho, Wo, stride);
   return hd::check_launch("subsample_kernel");
 }

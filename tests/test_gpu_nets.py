@@ -394,3 +394,17 @@ def test_conv1_from_padded_fp16_planes(n, size, tma, monkeypatch):
     rec = planes[0].float() + planes[1].float() / 2048.0
     assert float((rec[:, 3:3 + size, 3:3 + size, :3] - xt).abs().max()) < 1e-6
     assert float(rec[:, :3].abs().max()) == 0 and float(rec[:, :, :3].abs().max()) == 0 and float(rec[..., 3].abs().max()) == 0
+
+
+@pytest.mark.parametrize('n,H,C,s', [(3, 56, 256, 2), (5, 7, 128, 2), (2, 9, 64, 3), (1, 28, 512, 2)])
+def test_subsample_is_strided_slice(n, H, C, s):
+    """slim's identity shortcut of a strided unit: x[:, ::s, ::s, :] (pixel counts that are not multiples of the 4 pixels a warp copies)."""
+    from human_dynamics_b200._lib import lib, check, fptr
+    x = torch.randn((n, H, H, C), device='cuda')
+    Ho = (H - 1) // s + 1
+    out = torch.full((n, Ho, Ho, C), float('nan'), device='cuda')
+    guard = torch.zeros(64, device='cuda')          # directly behind `out` in most allocators; the tail warp must not write past the end
+    check(lib.hd_subsample(fptr(x), fptr(out), n, H, H, C, s, torch.cuda.current_stream().cuda_stream), 'hd_subsample')
+    torch.cuda.synchronize()
+    assert torch.equal(out, x[:, ::s, ::s, :].contiguous())
+    assert float(guard.abs().sum()) == 0.0
