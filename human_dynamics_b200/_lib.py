@@ -41,6 +41,9 @@ class ConvDesc(C.Structure):
     ]
 
 
+WEIGHT_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_longlong))      # hd_weight_fn
+
+
 class SmplConsts(C.Structure):
     """Mirror of hd_smpl_consts."""
     _fields_ = [
@@ -76,6 +79,15 @@ SIGNATURES = {
     'hd_ief_fc1_theta': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     'hd_ief_fc3': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     'hd_ief_delta_init': (_i, [_vp, _vp, _i, _i, _vp]),
+    'hd_net_destroy': (None, [_vp]),
+    'hd_net_error': (C.c_char_p, [_vp]),
+    'hd_net_num_launches': (_ll, [_vp]),
+    'hd_resnet50_create': (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    'hd_resnet50_forward': (_i, [_vp, _vp, _vp, _vp]),
+    'hd_fmovie_create': (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_vp)]),
+    'hd_fmovie_forward': (_i, [_vp, _vp, _vp, _vp]),
+    'hd_ief_create': (_i, [_vp, _vp, _i, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    'hd_ief_forward': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'hd_smpl_workspace_bytes': (_sz, [_i]),
     'hd_smpl_forward': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'hd_smpl_pose': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),

@@ -164,6 +164,31 @@ int hd_ief_fc3(const float *h2, const float *W, const float *bias, const float *
 /* ---- IEF glue (src/models.py:349-371): dst[n*dst_ld + :85] = [1, 0, 0, theta[n,3:75], theta[n,75:85]] ---- */
 int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *stream);
 
+/* ---- network-level entries: library-owned layer plans for the three networks on the path ----
+ * A plan packs the TF-named weights once (BatchNorm folded, K-major fp16 head / remainder split, TMA descriptors) and owns its
+ * activation buffers: `*_create` allocates device memory and copies weights (synchronous, once); `*_forward` is a fixed sequence of
+ * the per-layer entries above on `stream` -- no allocation, no synchronisation -- and is bit-identical to the Python host plans
+ * (human_dynamics_b200/nets.py).  Precision mode: HD_IMPL_TC_3XF16 (FP32-class).
+ * Weights are pulled through a callback: get(user, "<TF variable name>", &numel) returns a HOST pointer to the fp32 array in the
+ * TensorFlow layout (conv HWIO, FC [in,out]) -- e.g. "resnet_v2_50/block1/unit_1/bottleneck_v2/conv1/weights" -- or NULL if absent
+ * (then create fails with HD_ERR_INVALID and hd_net_error names the variable). */
+typedef struct hd_net hd_net;
+typedef const float *(*hd_weight_fn)(void *user, const char *tf_name, long long *numel);
+void hd_net_destroy(hd_net *net);
+const char *hd_net_error(const hd_net *net);
+long long hd_net_num_launches(const hd_net *net);
+/* encoder_resnet (src/models.py:50-77): images [n_frames,size,size,3] fp32 in [-1,1] -> phi [n_frames,2048].  size even. */
+int hd_resnet50_create(hd_weight_fn get, void *user, int n_frames, int size, hd_net **net);
+int hd_resnet50_forward(hd_net *net, const float *images, float *phi, void *stream);
+/* az_fc2_groupnorm (src/models.py:121-228): phi [B,T,2048] -> movie strips [B,T,2048] (out != phi).  T <= 20. */
+int hd_fmovie_create(hd_weight_fn get, void *user, int B, int T, int num_conv_layers, hd_net **net);
+int hd_fmovie_forward(hd_net *net, const float *phi, float *out, void *stream);
+/* call_hmr_ief (src/models.py:299-415) as wired by tester.py:196-207 (scope single_view_ief, 3 stages, use_optcam, deltas started
+ * from the main prediction): phi [N,2048] -> theta [N,85] and, for the num_delta non-zero delta_t values in ascending order,
+ * deltas [N,num_delta,85] = [1,0,0 | pose | beta].  IEF starts from the checkpoint's `mean_param`. */
+int hd_ief_create(hd_weight_fn get, void *user, int N, const int *delta_t, int num_delta, hd_net **net);
+int hd_ief_forward(hd_net *net, const float *phi, float *theta, float *deltas, void *stream);
+
 /* ---- SMPL (src/tf_smpl/batch_smpl.py:26-162, batch_lbs.py:15-60,133-194, projection.py:16-29) ---- */
 typedef struct {
   int num_verts, num_kps, lbs_nnz, kp_nnz_total;
