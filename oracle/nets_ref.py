@@ -1,10 +1,13 @@
 """ORACLE (test infrastructure, not product): CPU restatement of the HMMR networks.
 
-PARITY UNPINNED: TensorFlow 1.8 (requirements.txt:11) cannot be imported here and the
-reference holds no golden vectors for this path.  The first-party wiring
-follows the cited reference lines; the arithmetic that lives inside tf.contrib.slim /
-tf.contrib.layers of TF 1.8 is restated from its published semantics.  Each such
-ASSUMPTION is listed here and has its own focused unit test in tests/test_oracle_nets.py:
+PARITY STATUS: pinned to the reference's SOURCE, unpinned against TensorFlow's KERNELS.  TensorFlow 1.8
+(requirements.txt:11) cannot be imported here and the reference holds no golden vectors for this path
+(SURVEY.md 8c).  The first-party wiring (src/models.py, omega.py, tester.py) is checked against vectors made
+by executing those reference files themselves over a numpy TensorFlow stand-in (oracle/ref_exec/,
+tests/golden/ref_exec_v1.npz, tests/test_ref_exec.py: all 14 Tester.predict keys within 8.5e-6).  The
+arithmetic that lives inside tf.contrib.slim / tf.contrib.layers of TF 1.8 [TF-ext] is not part of
+/root/reference; it is restated from its published semantics here AND in the stand-in, so it stays an
+assumption.  Each such ASSUMPTION is listed here and has its own focused unit test in tests/test_oracle_nets.py:
 
   A1  SAME padding: out=ceil(in/s); pad_total=max((out-1)*s+k-in,0); extra pad at the END.
   A2  resnet_utils.conv2d_same: stride 1 -> SAME; stride>1 -> explicit pad (k-1)//2 each side + VALID.

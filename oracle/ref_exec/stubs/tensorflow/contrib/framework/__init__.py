@@ -15,3 +15,7 @@ def get_variables(scope=None, suffix=None, collection=None):
 
 
 get_variables_to_restore = get_variables
+
+
+def get_trainable_variables(scope=None, suffix=None):
+    return [v for v in get_variables(scope, suffix) if v.trainable]

@@ -1,6 +1,8 @@
 /*
  * ORACLE (test infrastructure, not product): plain-C restatement of the reference SMPL path, independent of the numpy
- * one in smpl_ref.py (tests/test_oracle_c.py checks the two against each other).  PARITY UNPINNED (TF 1.8 cannot run here).
+ * one in smpl_ref.py (tests/test_oracle_c.py checks the two against each other).  PARITY: pinned to the
+ * reference's source through smpl_ref.py (which is checked against src/tf_smpl/*.py executed over the numpy TensorFlow stand-in,
+ * oracle/ref_exec/); unpinned against TensorFlow's own kernels (TF 1.8 cannot run here).
  * Every function follows the cited reference lines; REAL selects float (TF-faithful) or double (truth).
  *
  *   gcc -O2 -shared -fPIC -DREAL=double -o liboracle_smpl_f64.so smpl_ref.c -lm

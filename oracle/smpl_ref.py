@@ -1,9 +1,13 @@
 """ORACLE (test infrastructure, not product): CPU restatement of the reference SMPL path.
 
-PARITY UNPINNED: the reference ships no tests / golden vectors for this path and TF 1.8
-cannot be imported here.  Every function follows the cited reference lines
-op by op (same operation order, so float32 rounding is comparable); `dtype` selects the
-float64 "truth" or the float32 "TF-faithful" variant.
+PARITY STATUS: pinned to the reference's SOURCE, unpinned against TensorFlow's KERNELS.  The reference ships
+no tests / golden vectors for this path and TF 1.8 cannot be imported here; instead
+src/tf_smpl/{batch_lbs,batch_smpl,projection}.py are executed unmodified over a numpy TensorFlow stand-in
+(oracle/ref_exec/) and this module is checked against their output (tests/golden/ref_exec_v1.npz,
+tests/test_ref_exec.py: verts / joints / Rs / FK / projection within 2e-5, regenerated live where
+/root/reference exists).  The SMPL path uses only core tf ops (matmul, reshape, tile, pad, scatter_nd, ...),
+no tf.contrib layer.  Every function follows the cited reference lines op by op (same operation order, so
+float32 rounding is comparable); `dtype` selects the float64 "truth" or the float32 "TF-faithful" variant.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this module.  The product path (human_dynamics_b200/, src/) never does.

@@ -1,6 +1,7 @@
 """Generates tests/golden/hmmr_golden_v1.npz from the CPU oracle on seeded synthetic inputs.
 
-PARITY UNPINNED: these vectors come from the oracle restatement (float64 variant), not from the reference's TF1
+REGRESSION PIN OF THE ORACLE (the reference-derived vectors are ref_exec_v1.npz, made by make_ref_exec_golden.py): these vectors
+come from the oracle restatement (float64 variant), not from the reference's TF1
 graph -- TensorFlow 1.8 cannot be imported in this environment.  They freeze the oracle so that a
 change to it is noticed, and give the GPU tests a fixture that needs no oracle run.  Inputs are NOT stored: they are
 regenerated from seeds by human_dynamics_b200.synthetic (weights seed 1, SMPL seed 2, images seed 11, SMPL inputs seed 12).

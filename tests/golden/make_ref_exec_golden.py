@@ -3,6 +3,7 @@
     src/tf_smpl/batch_lbs.py, batch_smpl.py, projection.py      (batch_rodrigues, batch_rot2aa, FK, SMPL.__call__, projection)
     src/models.py                                               (encoder_resnet, az_fc2_groupnorm, fc2_res, batch_pred_omega -> IEF)
     src/omega.py, src/evaluation/tester.py                      (Tester.__init__ / build_test_model / predict / predict_all_images)
+    src/datasets/resnet_extractor.py                            (FeatureExtractor: restore + compute_all_phis with a ragged last batch)
     src/evaluation/run_video.py + src/util/common.py            (process_image, resize_img)
     src/evaluation/eval_util.py                                 (metrics)
 
@@ -228,6 +229,21 @@ def gen_tester(out, syn, ckpt, weights, smpl, tmp):
     tf.reset_default_graph()
 
 
+def gen_feature_extractor(out, syn, ckpt, weights, tmp):
+    """resnet_extractor.py:13-98: placeholder of batch_size frames, Saver() over every variable of the graph, zero-padded last batch."""
+    import tensorflow as tf
+    from src.datasets.resnet_extractor import FeatureExtractor
+    tf.reset_default_graph()
+    prefix = os.path.join(tmp, 'resnet.ckpt-7')
+    ckpt.save_checkpoint(prefix, {k: np.ascontiguousarray(v, np.float32) for k, v in weights.items() if k.startswith('resnet_v2_50/')})
+    fe = FeatureExtractor(prefix, img_size=64, batch_size=4)
+    frames = syn.make_images(6, seed=61, size=64)                      # 6 frames, batch 4 -> second batch is 2 frames + 2 zero frames
+    out['fe_phis'] = np.asarray(fe.compute_all_phis(frames))
+    assert out['fe_phis'].shape == (6, 2048)
+    out['fe_restored_var_names'] = np.array(sorted(fe.saver.restored))
+    tf.reset_default_graph()
+
+
 def gen_process_image(out, tmp):
     import cv2
     from src.evaluation.run_video import process_image
@@ -280,6 +296,19 @@ def main():
     smpl = syn.make_synthetic_smpl(seed=2)
     tmp = tempfile.mkdtemp(prefix='ref_exec_')
     out = {'vert_ids': VERT_IDS}
+    path = os.path.join(ROOT, 'tests', 'golden', 'ref_exec_v1.npz')
+    only = os.environ.get('HD_REF_EXEC_ONLY')           # e.g. "feature_extractor": re-run one cheap section, keep the rest of the file
+    if only:
+        with np.load(path) as z:
+            out = {k: z[k] for k in z.files}
+        try:
+            {'feature_extractor': lambda: gen_feature_extractor(out, syn, ckpt, weights, tmp),
+             'process_image': lambda: gen_process_image(out, tmp), 'eval_util': lambda: gen_eval_util(out)}[only]()
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        np.savez_compressed(path, **out)
+        print('updated section', only, 'of', path, os.path.getsize(path), 'bytes,', len(out), 'arrays')
+        return
     try:
         smpl_pkl = os.path.join(tmp, 'smpl.pkl')
         write_smpl_pickle(smpl, smpl_pkl)
@@ -290,11 +319,11 @@ def main():
         print('models done', flush=True)
         gen_tester(out, syn, ckpt, weights, smpl, tmp)
         print('tester done', flush=True)
+        gen_feature_extractor(out, syn, ckpt, weights, tmp)
         gen_process_image(out, tmp)
         gen_eval_util(out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    path = os.path.join(ROOT, 'tests', 'golden', 'ref_exec_v1.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes,', len(out), 'arrays')
 

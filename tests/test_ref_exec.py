@@ -144,6 +144,16 @@ def test_oracle_full_tester_matches_reference_source(gold, weights, smpl_model):
     assert rel_err(rh['kps'], gold['hal_kps']) < 3e-5
 
 
+def test_oracle_feature_extractor_matches_reference_source(gold, weights):
+    """resnet_extractor.py executed from the reference: 6 frames through a batch-4 placeholder (zero-padded tail, :88-92)."""
+    from human_dynamics_b200 import synthetic
+    from oracle import nets_ref
+    frames = synthetic.make_images(6, seed=61, size=64)
+    assert rel_err(nets_ref.encoder_resnet(frames, weights).numpy(), gold['fe_phis']) < REL_ORACLE     # frames are independent
+    names = set(str(n) for n in gold['fe_restored_var_names'])
+    assert names == set(k for k in weights if k.startswith('resnet_v2_50/'))       # Saver() restores exactly the ResNet variables
+
+
 def test_process_image_oracle_matches_reference_source(gold):
     """run_video.py:56-107 executed from the reference (PNG round trip through its imread) vs oracle/preproc_ref.py."""
     sys.path.insert(0, os.path.join(HERE, 'golden'))
@@ -273,6 +283,18 @@ def test_cuda_hal_mode_matches_reference_source(gold, weights, smpl_model):
     r = t.predict(_tester_images()[:1, :4])
     assert rel_err(r['omegas'], gold['hal_omegas']) < REL and rel_err(r['omegas_delta'], gold['hal_omegas_delta']) < REL
     assert rel_err(r['kps'], gold['hal_kps']) < REL
+
+
+@pytest.mark.gpu
+def test_cuda_feature_extractor_matches_reference_source(gold, weights):
+    """Drop-in src.datasets.resnet_extractor.FeatureExtractor (ragged last batch) vs the reference's, executed from its source."""
+    from human_dynamics_b200 import synthetic
+    from src.datasets.resnet_extractor import FeatureExtractor
+    fe = FeatureExtractor({k: v for k, v in weights.items() if k.startswith('resnet_v2_50/')}, img_size=64, batch_size=4)
+    phis = fe.compute_all_phis(synthetic.make_images(6, seed=61, size=64))
+    assert phis.shape == (6, 2048) and rel_err(phis, gold['fe_phis']) < REL
+    with pytest.raises(ValueError):
+        fe.compute_phis(np.zeros((3, 64, 64, 3), np.float32))        # static batch like the TF placeholder
 
 
 @pytest.mark.gpu
