@@ -49,7 +49,11 @@ struct Cfg {
   // TEPI 1: full staging ring (fp32 residual / output + fp16 pair), 2 operand stages.  TEPI 2: layers that write ONLY the fp16 pair
   // and add no residual (conv1 / conv2 of a bottleneck: long K, tensor-bound): 16 KB slabs, one buffer per drain group, which leaves
   // room for the third operand stage their main loop wants.
-  static constexpr int STAGES = (DUAL || TEPI == 1) ? 2 : 3;
+  // 64-wide tiles (conv1 of the root, the 64-channel layers of block 1, the few-tile head GEMMs) have 48 KB stages: their main loops are
+  // load-LATENCY-bound (per-role counters, profiles/r02_roles_plan_layers.txt: ~1450 cycles per chunk against 393 cycles of tensor
+  // time and ~940 of shared-memory port time with 2-3 chunks in flight), so they trade staging buffers for operand stages:
+  // TEPI 1: 3 stages + a ring of 2 (215 KB), TEPI 2: 4 stages + its ring of 2 (226 KB).
+  static constexpr int STAGES = DUAL ? 2 : (TEPI == 1 ? (BN == 64 ? 3 : 2) : ((TEPI == 2 && BN == 64) ? 4 : 3));
   static constexpr int DW = (DUAL || TEPI) ? 8 : 4;             // drain + epilogue warps (DUAL: two groups on alternate tiles;
                                                                 // TEPI: two groups on alternate 32-column slabs of the same tile)
   static constexpr int NUM_THREADS = (DW + 8 + 4) * 32;         // + 8 producer warps + {TMA, MMA, 2 idle}
@@ -65,11 +69,12 @@ struct Cfg {
   static constexpr int LUT_OFFSET = STG_OFFSET + STG_BYTES;      // GATHER: k -> (ky, kx, offset) table, 256 entries
   // TEPI staging ring: per buffer one fp32 slab [128][32] (128-byte rows, SWIZZLE_128B) + two fp16 slabs [128][32]
   // (64-byte rows, SWIZZLE_64B); 1024-byte aligned
-  static constexpr int EPI_NB = TEPI == 2 ? 2 : 3;
+  static constexpr int EPI_NB = (TEPI == 2 || (TEPI == 1 && BN == 64)) ? 2 : 3;
   static constexpr int EPI_F32_BYTES = TEPI == 2 ? 0 : 128 * 128, EPI_H_BYTES = 128 * 64;
   static constexpr int EPI_BUF_BYTES = EPI_F32_BYTES + 2 * EPI_H_BYTES;
   static constexpr int EPI_OFFSET = (BAR_OFFSET + 128 + 1023) / 1024 * 1024;
   static constexpr int SMEM_BYTES = TEPI ? EPI_OFFSET + EPI_NB * EPI_BUF_BYTES + 1024 : LUT_OFFSET + 1024 + 1024;   // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "dynamic shared memory beyond the 227 KB a CTA can opt into");
   static constexpr int TMEM_COLS = 4 * BN;                      // 2 cross-term + 2 ping-pong accumulators (512 / 256)
   // D=f32, A/B K-major: c_format[4,6)=1, a_format[7,10), b_format[10,13) (2 = TF32, 0 = F16), N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t FMT = HALF ? 0u : 2u;
