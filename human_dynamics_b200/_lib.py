@@ -38,6 +38,7 @@ class ConvDesc(C.Structure):
         ('tmap_res', C.c_void_p), ('tmap_out', C.c_void_p), ('tmap_out_hi', C.c_void_p), ('tmap_out_lo', C.c_void_p),
         ('flags', C.c_int),
         ('tmap_hi_n64', C.c_void_p), ('tmap_lo_n64', C.c_void_p),
+        ('out_subsample', C.c_int),
     ]
 
 

@@ -18,6 +18,7 @@ struct ConvParams {
   const void *in_hi, *in_lo;      // pre-split fp16 activations (cp.async producer) or nullptr
   void *out_hi, *out_lo; long long out2_ld;
   const float *post2_scale, *post2_shift; int post2_relu;
+  int out_sub;     // > 1: `out` is the dense [n, ceil(Ho/s), ceil(Wo/s), Cout] subsample, only rows with oy % s == 0 && ox % s == 0 are written
   int planes;      // A operand = padded RGBX fp16 planes of the resnet conv1 input (see conv_tc.cu producer)
   long long *dbg;  // optional: per-role cycle counters of CTA (0,0) (hd_conv_gemm_profile), else nullptr
 };
@@ -76,6 +77,8 @@ inline int fill_params(const hd_conv_desc *d, ConvParams &p) {
               (!d->post_scale || aligned16(d->post_scale)) && (!d->post_shift || aligned16(d->post_shift));
   p.K_pad = d->K_pad;
   p.planes = (d->flags & HD_CONV_INPUT_PLANES) ? 1 : 0;
+  p.out_sub = d->out_subsample > 1 ? d->out_subsample : 0;
+  if (p.out_sub && !d->out) { set_last_error_text("hd_conv_gemm: out_subsample needs `out`"); return HD_ERR_INVALID; }
   p.dbg = nullptr;
   return HD_OK;
 }

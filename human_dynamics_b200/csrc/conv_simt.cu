@@ -217,6 +217,10 @@ int launch(const ConvParams &p, cudaStream_t st) {
 }  // namespace
 
 int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
+  if (p.out_sub) {
+    set_last_error_text("hd_conv_gemm(simt): out_subsample is only implemented by the tensor-core TMA epilogue");
+    return HD_ERR_UNSUPPORTED;
+  }
   if (!p.w_kn || !p.in || !p.out || p.out_hi) {
     set_last_error_text("hd_conv_gemm(simt): needs w_kn and fp32 in/out (no pre-split activations)");
     return HD_ERR_INVALID;

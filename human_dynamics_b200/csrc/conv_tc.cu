@@ -685,7 +685,22 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
         constexpr int NSL = BN / 32, NB = C::EPI_NB;
         const int row = quarter * 32 + lane;
         const uint32_t sw128 = (uint32_t)(row & 7), sw64 = (uint32_t)((row >> 1) & 3);
-        const bool has_res = p.res != nullptr, has_o32 = p.out != nullptr, has_o16 = p.out_hi != nullptr;
+        const bool has_res = p.res != nullptr, has_o32 = p.out != nullptr && !p.out_sub, has_o16 = p.out_hi != nullptr;
+        // out_sub: this thread's row goes to the dense subsampled fp32 output iff its pixel is (oy % s == 0, ox % s == 0); one pair of
+        // divisions per tile, then eight 16-byte stores per slab straight from the registers (a quarter of the threads, 128 contiguous
+        // bytes each) -- the fp32 slab is neither staged for nor stored by TMA
+        float *sub_row = nullptr;
+        if (p.out_sub) {
+          const int m = m0 + row;
+          if (m < p.M) {
+            const int n = m / hw, r = m - n * hw;
+            const int oy = r / p.Wo, ox = r - oy * p.Wo;
+            if (oy % p.out_sub == 0 && ox % p.out_sub == 0) {
+              const int Hs = (p.Ho + p.out_sub - 1) / p.out_sub, Ws = (p.Wo + p.out_sub - 1) / p.out_sub;
+              sub_row = p.out + ((size_t)((size_t)n * Hs + oy / p.out_sub) * Ws + ox / p.out_sub) * p.out_ld + n0;
+            }
+          }
+        }
 #pragma unroll
         for (int s2 = 0; s2 < NSL / 2; ++s2) {
           const int sl = s2 * 2 + dgroup;               // this group's slabs: dgroup, dgroup + 2
@@ -723,6 +738,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
               }
               if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               if (has_o32) *sp = v;
+              if (sub_row) *reinterpret_cast<float4 *>(sub_row + sl * 32 + 4 * c) = v;
               y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
             }
             if (has_o16) {       // the next layer's A operand: second affine (+ReLU) = its pre-activation, split into fp16 head/remainder
@@ -820,7 +836,7 @@ conv_gemm_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
           mbar_wait(ready_bar(b), (uint32_t)(j / NB) & 1u);
           const uint32_t sb = smem_base + C::EPI_OFFSET + b * C::EPI_BUF_BYTES;
           if (c0 < p.Cout) {
-            if (p.out) tma_store_2d(&em.out, sb, c0, c1);
+            if (p.out && !p.out_sub) tma_store_2d(&em.out, sb, c0, c1);
             if (p.out_hi) {
               tma_store_2d(&em.ohi, sb + C::EPI_F32_BYTES, c0, c1);
               tma_store_2d(&em.olo, sb + C::EPI_F32_BYTES + C::EPI_H_BYTES, c0, c1);
@@ -970,6 +986,10 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
   }
   const bool half = d->impl == HD_IMPL_TC_3XF16;
   const int bke = half ? 64 : 32;
+  if (p.out_sub && (!p.in_hi || p.planes)) {
+    set_last_error_text("hd_conv_gemm: out_subsample is only implemented by the TMA epilogue (pre-split input, Cout % 32 == 0, activation maps given)");
+    return HD_ERR_UNSUPPORTED;
+  }
   if ((p.out_hi || p.in_hi) && (!half || !p.vec_out)) {
     set_last_error_text("hd_conv_gemm(tc): pre-split activations need impl 3 and 16-byte aligned, 4-column-multiple outputs");
     return HD_ERR_INVALID;
@@ -995,7 +1015,7 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
       // accumulations, ~4e-7 relative).  HD_TEPI_MAXK (env) restricts it to K <= that value (A/B switch; 256 = round-2 first cut).
       static const int tepi_maxk = [] { const char *e = getenv("HD_TEPI_MAXK"); return e ? atoi(e) : (1 << 30); }();
       const bool res_plain = !p.res || (p.res_stride == 1 && p.res_H == p.Ho && p.res_W == p.Wo);
-      const bool maps = (!p.res || d->tmap_res) && (!p.out || d->tmap_out) && (!p.out_hi || (d->tmap_out_hi && d->tmap_out_lo));
+      const bool maps = (!p.res || d->tmap_res) && (!p.out || p.out_sub || d->tmap_out) && (!p.out_hi || (d->tmap_out_hi && d->tmap_out_lo));
       if (maps && res_plain && p.Cout % 32 == 0 && !(d->flags & HD_CONV_NO_TMA_EPILOGUE) && (p.K <= 256 || p.K <= tepi_maxk))
       {
         // few-tile GEMMs (IEF FCs at 640 rows: 40 tiles of 128x128 for 148 SMs): 64-wide tiles double the CTA count
@@ -1011,6 +1031,10 @@ int launch_conv_tc(const ConvParams &p, const hd_conv_desc *d, cudaStream_t st) 
         return narrow ? launch_tc<64, true, 4, true, false, true, false, 1>(p, d, st)
                       : launch_tc<128, true, 4, true, false, true, false, 1>(p, d, st);
       }
+    }
+    if (p.out_sub) {
+      set_last_error_text("hd_conv_gemm: out_subsample is only implemented by the TMA epilogue (pre-split input, Cout % 32 == 0, activation maps given)");
+      return HD_ERR_UNSUPPORTED;
     }
     if (p.K <= 256)      // (strided-subsample residuals / no tensor maps) two drain/epilogue warp groups with per-thread global accesses
       return p.Cout <= 64 ? launch_tc<64, true, 4, true, false, true, true>(p, d, st) : launch_tc<128, true, 4, true, false, true, true>(p, d, st);

@@ -183,6 +183,7 @@ struct Builder {
     const float *res = nullptr;
     long long res_ld = 0;
     int res_H = 0, res_W = 0, res_stride = 1;
+    int out_subsample = 0;
   };
 
   bool bind(const PackedConv &c, const Bind &b, hd_conv_desc &d) {
@@ -197,6 +198,7 @@ struct Builder {
     d.post_scale = c.post_scale; d.post_shift = c.post_shift; d.post_relu = c.post_relu;
     if (b.res) { d.res = b.res; d.res_ld = b.res_ld; d.res_H = b.res_H; d.res_W = b.res_W; d.res_stride = b.res_stride; }
     d.out = b.out; d.out_ld = c.Cout;
+    d.out_subsample = b.out ? b.out_subsample : 0;
     if (b.out2.hi) {
       d.out_hi = b.out2.hi; d.out_lo = b.out2.lo; d.out2_ld = c.Cout;
       d.post2_scale = b.post2_scale; d.post2_shift = b.post2_shift; d.post2_relu = b.post2_relu;
@@ -217,7 +219,7 @@ struct Builder {
     F f[4] = {{d.res, d.res_ld, 4, &d.tmap_res}, {d.out, d.out_ld, 4, &d.tmap_out}, {d.out_hi, d.out2_ld, 2, &d.tmap_out_hi},
               {d.out_lo, d.out2_ld, 2, &d.tmap_out_lo}};
     for (auto &x : f) {
-      if (!x.ptr) continue;
+      if (!x.ptr || (x.slot == &d.tmap_out && d.out_subsample > 1)) continue;
       if (((uintptr_t)x.ptr % 16) || (x.ld * x.eb) % 16) {
         d.tmap_res = d.tmap_out = d.tmap_out_hi = d.tmap_out_lo = nullptr;
         return true;
@@ -404,6 +406,7 @@ int hd_resnet50_create(hd_weight_fn get, void *user, int n_frames, int size, hd_
   }
   float *x = bufA, *y = bufB;
   int H = H2;
+  bool sub_ready = false;              // bufS already holds x[:, ::s, ::s] of the current unit's input
   for (size_t ui = 0; ui < units.size() && b.rc == HD_OK; ++ui) {
     const Unit &un = units[ui];
     const int s = un.stride, Ho = (H - 1) / s + 1;
@@ -414,10 +417,12 @@ int hd_resnet50_create(hd_weight_fn get, void *user, int n_frames, int size, hd_
       if (!b.bind(un.shortcut, bs, d)) break;
       b.conv_step(d);
       res = bufS;
-    } else if (s > 1) {                                  // strided identity shortcut: dense subsampled copy (row-aligned residual)
-      const float *src = x;
-      const int Hh = H, Cc = un.depth;
-      net->steps.push_back([=](cudaStream_t st) { return hd_subsample(src, bufS, n, Hh, Hh, Cc, s, (void *)st); });
+    } else if (s > 1) {                                  // strided identity shortcut: dense subsampled copy (row-aligned residual),
+      if (!sub_ready) {                                  // written by the previous unit's conv3 epilogue (out_subsample) when possible
+        const float *src = x;
+        const int Hh = H, Cc = un.depth;
+        net->steps.push_back([=](cudaStream_t st) { return hd_subsample(src, bufS, n, Hh, Hh, Cc, s, (void *)st); });
+      }
       res = bufS;
     } else {
       res = x;
@@ -431,10 +436,16 @@ int hd_resnet50_create(hd_weight_fn get, void *user, int n_frames, int size, hd_
     const bool last = ui + 1 == units.size();
     Builder::Bind b3; b3.n = n; b3.H = Ho; b3.W = Ho; b3.in = r2;
     b3.res = res; b3.res_ld = un.depth; b3.res_H = Ho; b3.res_W = Ho; b3.res_stride = 1;
+    sub_ready = false;
     if (!last) {
       b3.out2 = ys; b3.post2_scale = units[ui + 1].pre_scale; b3.post2_shift = units[ui + 1].pre_shift; b3.post2_relu = 1;
       // the fp32 block output only feeds an IDENTITY shortcut; skip it when the next unit's shortcut is a conv
       b3.out = units[ui + 1].has_shortcut ? nullptr : y;
+      // ... and when that identity shortcut is strided only x[:, ::s, ::s] is ever read: write just those pixels, densely, into bufS
+      if (b3.out && units[ui + 1].stride > 1 && !un.has_shortcut && s == 1) {
+        sub_ready = true;
+        b3.out = bufS; b3.out_subsample = units[ui + 1].stride;
+      }
     } else {
       b3.out = y;
     }

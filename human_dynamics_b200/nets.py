@@ -120,10 +120,11 @@ class PackedConv(object):
             self.tc = want
 
     def bind(self, inp, n_img, H, W, out, in_ld=None, out_ld=None, pre=None, res=None, res_geom=None, impl='auto',
-             inp_split=None, out_split=None, post2=None):
+             inp_split=None, out_split=None, post2=None, out_subsample=0):
         """Fill a descriptor.  inp/out/res: CUDA float32 tensors (only their data_ptr is used).
 
         pre = (scale, shift, img_stride, relu); res_geom = (res_ld, res_H, res_W, res_stride).
+        out_subsample = s > 1: `out` is the dense [n, ceil(Ho/s), ceil(Wo/s), Cout] tensor x[:, ::s, ::s] (hd_b200.h);
         inp_split = (hi, lo) fp16 tensors: pre-activated, pre-split A operand (then `inp` may be None);
         out_split = (hi, lo) fp16 tensors + post2 = (scale|None, shift|None, relu): second output (then `out` may be None).
         """
@@ -155,6 +156,7 @@ class PackedConv(object):
             d.res_ld, d.res_H, d.res_W, d.res_stride = res_geom
         d.out = out.data_ptr() if out is not None else None
         d.out_ld = self.Cout if out_ld is None else out_ld
+        d.out_subsample = int(out_subsample) if out is not None else 0
         if out_split is not None:
             d.out_hi, d.out_lo, d.out2_ld = out_split[0].data_ptr(), out_split[1].data_ptr(), self.Cout
             if post2 is not None:
@@ -207,6 +209,7 @@ class SubsampleOp(object):
 
 
 SUBSAMPLE_RES = os.environ.get('HD_SUBSAMPLE_RES', '1') != '0'    # A/B switch: strided identity shortcuts via hd_subsample + plain residual
+SUBSAMPLE_EPI = os.environ.get('HD_SUBSAMPLE_EPI', '1') != '0'    # A/B switch: the unit in front of a strided identity unit writes x[:, ::s, ::s] itself
 TMA_EPILOGUE = os.environ.get('HD_TMA_EPILOGUE', '1') != '0'     # A/B switch for the K <= 256 layers (results identical)
 
 
@@ -236,7 +239,7 @@ class ConvOp(object):
             self.maps = {f: (C.c_ubyte * 128)() for f in ('res', 'out', 'out_hi', 'out_lo')}
         for f, ptr, ld, eb in (('res', d.res, d.res_ld, 4), ('out', d.out, d.out_ld, 4), ('out_hi', d.out_hi, d.out2_ld, 2),
                                ('out_lo', d.out_lo, d.out2_ld, 2)):
-            if not ptr:
+            if not ptr or (f == 'out' and d.out_subsample > 1):
                 continue
             if ptr % 16 or (ld * eb) % 16:
                 for g in ('tmap_res', 'tmap_out', 'tmap_out_hi', 'tmap_out_lo'):
@@ -420,6 +423,7 @@ class ResNetPlan(object):
                 self.pool_split = (units[0]['pre'][0], units[0]['pre'][1], xs)
                 self.pool_f32_dead = DROP_DEAD_FP32 and 'shortcut' in units[0]
             self.out_split = None
+            sub_ready = False                 # bufS already holds x[:, ::s, ::s] of this unit's input (written by the previous conv3)
             for ui, unit in enumerate(units):
                 s = unit['stride']
                 Ho = (H - 1) // s + 1
@@ -429,10 +433,12 @@ class ResNetPlan(object):
                         self.in_refs += [(self.ops[-1], 'in_hi', 0), (self.ops[-1], 'in_lo', 1)]
                     res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
                 elif s > 1 and SUBSAMPLE_RES:
-                    # strided identity shortcut: subsample once into a dense buffer so conv3's residual is row-aligned (TMA slab loads)
-                    self.ops.append(SubsampleOp(x, self.bufS[:n * Ho * Ho * unit['depth']], n, H, unit['depth'], s))
-                    if ui == 0:
-                        self.in_refs.append((self.ops[-1], 'res', 2))
+                    # strided identity shortcut: a dense subsampled copy so conv3's residual is row-aligned (TMA slab loads) -- written by
+                    # the previous unit's conv3 epilogue when that unit is in this plan, else by one hd_subsample pass
+                    if not sub_ready:
+                        self.ops.append(SubsampleOp(x, self.bufS[:n * Ho * Ho * unit['depth']], n, H, unit['depth'], s))
+                        if ui == 0:
+                            self.in_refs.append((self.ops[-1], 'res', 2))
                     res, res_geom = self.bufS, (unit['depth'], Ho, Ho, 1)
                 else:
                     res, res_geom = x, (unit['depth'], H, H, s)
@@ -447,8 +453,16 @@ class ResNetPlan(object):
                 # shortcut is a conv of the pre-activation, and the fp32 copy would be written for nobody
                 nxt_conv_shortcut = ('shortcut' in units[ui + 1]) if not last else bool(next_has_shortcut)
                 y_out = None if (osplit is not None and nxt_conv_shortcut and DROP_DEAD_FP32) else y
+                # the next unit is a strided identity unit: the only reader of this unit's fp32 output is that shortcut, x[:, ::s, ::s]
+                # -- write just those pixels, densely, into bufS (free here: this unit's own residual is not in bufS)
+                s_next = units[ui + 1]['stride'] if not last else 1
+                sub_ready = bool(SUBSAMPLE_EPI and SUBSAMPLE_RES and not last and s_next > 1 and 'shortcut' not in units[ui + 1] and
+                                 'shortcut' not in unit and s == 1 and y_out is not None and osplit is not None)
+                if sub_ready:
+                    y_out = self.bufS
                 self.ops.append(unit['conv3'].bind(None, n, Ho, Ho, y_out, inp_split=r2, res=res, res_geom=res_geom, impl=impl,
-                                                   out_split=osplit, post2=(nxt[0], nxt[1], 1) if nxt is not None else None))
+                                                   out_split=osplit, post2=(nxt[0], nxt[1], 1) if nxt is not None else None,
+                                                   out_subsample=s_next if sub_ready else 0))
                 if ui == 0 and 'shortcut' not in unit and not (s > 1 and SUBSAMPLE_RES):
                     self.in_refs.append((self.ops[-1], 'res', 2))
                 if last:

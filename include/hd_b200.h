@@ -88,6 +88,12 @@ typedef struct {
   /* optional second pair of weight maps with a 64-row box (hd_make_weight_tmap(..., box_rows = 64, ...)) for Cout > 64: lets a GEMM
    * with few 128x128 tiles (2 * tiles <= #SMs) run on 64-wide tiles, i.e. on twice as many CTAs. */
   const void *tmap_hi_n64, *tmap_lo_n64;
+  /* out_subsample = s > 1 (TMA-epilogue path only; HD_ERR_UNSUPPORTED elsewhere): `out` is a dense [n_img, ceil(Ho/s), ceil(Wo/s), Cout]
+   * tensor that receives only the output pixels with oy % s == 0 and ox % s == 0 -- i.e. x[:, ::s, ::s, :], slim's identity shortcut
+   * of the NEXT, strided unit (max_pool2d(x, [1,1], stride), A.4), written by the producing conv3 itself: the full-resolution fp32
+   * block output has no other reader (the next unit's convs read out_hi / out_lo), so 3/4 of it is never written and no separate
+   * hd_subsample pass runs.  out_ld is the row pitch of that dense tensor; tmap_out is not used.  0 / 1 = off. */
+  int out_subsample;
 } hd_conv_desc;
 
 enum {

@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_layouts_match_header_sizes():
     """hd_conv_desc / hd_smpl_consts mirrors: field counts and natural-alignment sizes."""
     from human_dynamics_b200 import _lib
-    assert ctypes.sizeof(_lib.ConvDesc) == 336
+    assert ctypes.sizeof(_lib.ConvDesc) == 344
     assert ctypes.sizeof(_lib.SmplConsts) == 16 + 9 * 8 + 24 * 4
     assert _lib.ConvDesc.in_ld.offset == 8 and _lib.ConvDesc.w_kn.offset == 64 and _lib.ConvDesc.out.offset == 176
 
@@ -73,7 +73,7 @@ def test_conv_desc_matches_compiled_struct():
         import pytest
         pytest.skip('gcc not available')
     fields = ['in_ld', 'w_kn', 'Cout', 'pre_scale', 'post_relu', 'res', 'out', 'impl', 'tmap_hi', 'in_hi', 'out_hi', 'out2_ld',
-              'post2_relu', 'tmap_res', 'tmap_out_lo', 'flags', 'tmap_lo_n64']
+              'post2_relu', 'tmap_res', 'tmap_out_lo', 'flags', 'tmap_lo_n64', 'out_subsample']
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "hd_b200.h"\nint main(){printf("%zu %zu", sizeof(hd_conv_desc), sizeof(hd_smpl_consts));\n'
     src += ''.join('printf(" %%zu", offsetof(hd_conv_desc, %s));\n' % f for f in fields) + 'return 0;}\n'
     with tempfile.TemporaryDirectory() as td:

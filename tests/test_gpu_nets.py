@@ -194,6 +194,38 @@ def test_resnet_matches_oracle(weights, impl, n, size):
     assert rel_err(phi.cpu().numpy(), ref) < REL
 
 
+@pytest.mark.parametrize('size', [224, 72])
+def test_resnet_epilogue_subsample_equals_subsample_pass(weights, monkeypatch, size):
+    """The unit in front of a strided identity unit writes x[:, ::s, ::s] from its conv3 epilogue (hd_conv_desc.out_subsample) instead of
+    the full fp32 map + an hd_subsample pass: same bits, three passes fewer (size 72 walks odd maps: 9 -> 5 -> 3)."""
+    from human_dynamics_b200 import synthetic, nets, _lib
+    from human_dynamics_b200.nets import PackedResNet, ResNetPlan, SubsampleOp
+    from oracle import nets_ref
+    dev = torch.device('cuda')
+    img_h = synthetic.make_images(3, seed=8, size=size)
+    img = torch.from_numpy(img_h).to(dev)
+    packed = PackedResNet(weights, dev, tc='auto')
+    outs = []
+    for epi in (True, False):
+        monkeypatch.setattr(nets, 'SUBSAMPLE_EPI', epi)
+        plan = ResNetPlan(packed, 3, size, 'auto')
+        assert plan.split
+        assert sum(isinstance(op, SubsampleOp) for op in plan.ops) == (0 if epi else 3)
+        assert sum(1 for op in plan.ops if getattr(op, 'd', None) is not None and op.d.out_subsample > 1) == (3 if epi else 0)
+        phi = torch.empty((3, 2048), dtype=torch.float32, device=dev)
+        plan.run(img, phi)
+        torch.cuda.synchronize()
+        outs.append(phi)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(outs[0].cpu().numpy(), nets_ref.encoder_resnet(img_h, weights).numpy()) < REL
+    # paths without the TMA epilogue refuse the flag instead of silently writing the full map
+    op = next(op for op in plan.ops if getattr(op, 'd', None) is not None and op.d.out and op.d.res)
+    op.d.out_subsample = 2
+    op.d.flags |= _lib.HD_CONV_NO_TMA_EPILOGUE
+    assert _lib.lib.hd_conv_gemm(op.ref, _lib.current_stream()) == 4          # HD_ERR_UNSUPPORTED
+    op.d.out_subsample = 0
+
+
 def test_resnet_dead_fp32_outputs_are_dead(weights, monkeypatch):
     """Skipping the fp32 copies nobody reads (pool1 output, block outputs in front of a conv shortcut) must not change a bit."""
     from human_dynamics_b200 import synthetic, nets
