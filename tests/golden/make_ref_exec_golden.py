@@ -229,6 +229,41 @@ def gen_tester(out, syn, ckpt, weights, smpl, tmp):
     tf.reset_default_graph()
 
 
+def gen_tester_three_deltas(out, syn, ckpt, smpl, tmp):
+    """Tester with three delta heads given in UNSORTED order (config.delta_t_values = ['10', '-5', '5']): the reference stacks the
+    `_delta` outputs in ascending delta_t order (`sorted(self.omegas_pred.items())`, tester.py:244) and names the scopes
+    `_past5` / `_future5` / `_future10` (models.py:344-347).  B=1, T=4, separate weights (seed 9)."""
+    import tensorflow as tf
+    from src.evaluation.tester import Tester
+    from src.omega import OmegasPred
+    tf.reset_default_graph()
+    OmegasPred.omega_instances[:] = []
+    w = syn.make_synthetic_weights(seed=9, delta_t_values=(-5, 5, 10))
+    smpl_pkl = os.path.join(tmp, 'neutral_smpl_with_cocoplus_reg.pkl')
+    if not os.path.exists(smpl_pkl):
+        write_smpl_pickle(smpl, smpl_pkl)
+    mp0 = syn.make_mean_param(seed=77)
+    np.savez(os.path.join(tmp, 'neutral_smpl_meanwjoints.npz'), pose=mp0[0, 3:75], shape=mp0[0, 75:])
+    smpl_vars, _ = smpl_checkpoint_vars(smpl)
+    tensors = {k: np.ascontiguousarray(v, np.float32) for k, v in w.items()}
+    tensors.update({k: np.ascontiguousarray(v, np.float32) for k, v in smpl_vars.items()})
+    prefix = os.path.join(tmp, 'model3.ckpt-3')
+    ckpt.save_checkpoint(prefix, tensors)
+    cfg = types.SimpleNamespace(load_path=prefix, batch_size=1, sequence_length=4, pred_mode='pred', num_conv_layers=3,
+                                delta_t_values=['10', '-5', '5'], smpl_model_path=smpl_pkl, num_kps=25)
+    t = Tester(cfg)
+    images = syn.make_images(4, seed=23, size=224).reshape(1, 4, 224, 224, 3)
+    r = t.predict(images)
+    assert np.asarray(r['omegas_delta']).shape == (1, 4, 3, 85)
+    out['three_omegas'] = np.asarray(r['omegas'])
+    out['three_omegas_delta'] = np.asarray(r['omegas_delta'])
+    out['three_kps_delta'] = np.asarray(r['kps_delta'])
+    out['three_verts_delta'] = np.asarray(r['verts_delta'])[:, :, :, VERT_IDS]
+    out['three_var_names'] = np.array(sorted(v.op_name for v in t.encoder_vars))
+    OmegasPred.omega_instances[:] = []
+    tf.reset_default_graph()
+
+
 def gen_feature_extractor(out, syn, ckpt, weights, tmp):
     """resnet_extractor.py:13-98: placeholder of batch_size frames, Saver() over every variable of the graph, zero-padded last batch."""
     import tensorflow as tf
@@ -303,6 +338,7 @@ def main():
             out = {k: z[k] for k in z.files}
         try:
             {'feature_extractor': lambda: gen_feature_extractor(out, syn, ckpt, weights, tmp),
+             'three_deltas': lambda: gen_tester_three_deltas(out, syn, ckpt, smpl, tmp),
              'process_image': lambda: gen_process_image(out, tmp), 'eval_util': lambda: gen_eval_util(out)}[only]()
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
@@ -319,6 +355,7 @@ def main():
         print('models done', flush=True)
         gen_tester(out, syn, ckpt, weights, smpl, tmp)
         print('tester done', flush=True)
+        gen_tester_three_deltas(out, syn, ckpt, smpl, tmp)
         gen_feature_extractor(out, syn, ckpt, weights, tmp)
         gen_process_image(out, tmp)
         gen_eval_util(out)

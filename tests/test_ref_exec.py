@@ -144,6 +144,31 @@ def test_oracle_full_tester_matches_reference_source(gold, weights, smpl_model):
     assert rel_err(rh['kps'], gold['hal_kps']) < 3e-5
 
 
+def _three_delta_inputs():
+    from human_dynamics_b200 import synthetic
+    w = synthetic.make_synthetic_weights(seed=9, delta_t_values=(-5, 5, 10))
+    img = synthetic.make_images(4, seed=23, size=224).reshape(1, 4, 224, 224, 3)
+    return w, img
+
+
+def test_oracle_three_delta_heads_match_reference_source(gold, smpl_model):
+    """config.delta_t_values = ['10', '-5', '5'] (unsorted): the reference stacks `_delta` outputs in ascending delta_t order."""
+    from oracle import nets_ref
+    w, img = _three_delta_inputs()
+    r = nets_ref.hmmr_predict(img, w, smpl_model, delta_t_values=(10, -5, 5))
+    ids = gold['vert_ids']
+    assert rel_err(r['omegas'], gold['three_omegas']) < 3e-5
+    assert rel_err(r['omegas_delta'], gold['three_omegas_delta']) < 3e-5
+    assert rel_err(r['kps_delta'], gold['three_kps_delta']) < 3e-5
+    assert rel_err(r['verts_delta'][:, :, :, ids], gold['three_verts_delta']) < 3e-5
+    d = gold['three_omegas_delta']
+    assert not np.allclose(d[:, :, 0], d[:, :, 1]) and not np.allclose(d[:, :, 1], d[:, :, 2])       # three different heads
+    names = set(str(n) for n in gold['three_var_names'])
+    for sc in ('single_view_ief_past5', 'single_view_ief_future5', 'single_view_ief_future10'):     # models.py:344-347
+        assert sc + '/3D_module/fc1/weights' in names
+    assert set(k for k in w) <= names
+
+
 def test_oracle_feature_extractor_matches_reference_source(gold, weights):
     """resnet_extractor.py executed from the reference: 6 frames through a batch-4 placeholder (zero-padded tail, :88-92)."""
     from human_dynamics_b200 import synthetic
@@ -273,6 +298,21 @@ def test_cuda_tester_matches_reference_source(gold, weights, smpl_model):
     for k in ('omegas', 'kps', 'joints', 'omegas_delta', 'cams_delta'):
         assert rel_err(ra[k], gold['window_' + k]) < REL, k
     assert rel_err(np.asarray(ra['verts'])[:, ids], gold['window_verts']) < REL
+
+
+@pytest.mark.gpu
+def test_cuda_three_delta_heads_match_reference_source(gold, smpl_model):
+    from human_dynamics_b200 import HMMRConfig
+    from src.evaluation.tester import Tester
+    w, img = _three_delta_inputs()
+    t = Tester(HMMRConfig(batch_size=1, sequence_length=4, weights=w, smpl_model=smpl_model, pred_mode='pred', delta_t_values=['10', '-5', '5']))
+    r = t.predict(img)
+    ids = gold['vert_ids']
+    assert np.asarray(r['omegas_delta']).shape == (1, 4, 3, 85)
+    assert rel_err(r['omegas'], gold['three_omegas']) < REL
+    assert rel_err(r['omegas_delta'], gold['three_omegas_delta']) < REL
+    assert rel_err(r['kps_delta'], gold['three_kps_delta']) < REL
+    assert rel_err(np.asarray(r['verts_delta'])[:, :, :, ids], gold['three_verts_delta']) < REL
 
 
 @pytest.mark.gpu
