@@ -177,7 +177,10 @@ int hd_ief_delta_init(const float *theta, float *dst, int dst_ld, int N, void *s
  * (human_dynamics_b200/nets.py).  Precision mode: HD_IMPL_TC_3XF16 (FP32-class).
  * Weights are pulled through a callback: get(user, "<TF variable name>", &numel) returns a HOST pointer to the fp32 array in the
  * TensorFlow layout (conv HWIO, FC [in,out]) -- e.g. "resnet_v2_50/block1/unit_1/bottleneck_v2/conv1/weights" -- or NULL if absent
- * (then create fails with HD_ERR_INVALID and hd_net_error names the variable). */
+ * (then create fails with HD_ERR_INVALID and hd_net_error names the variable); the arrays only have to stay valid during `*_create`.
+ * A plan is bound to the device that was current at creation and is not re-entrant: one `*_forward` at a time per hd_net (its
+ * activation buffers are the state); use one plan per stream for concurrency.  `*_forward` can be captured in a CUDA graph.
+ * hd_net_destroy frees the device memory immediately: synchronise the streams that used the plan first. */
 typedef struct hd_net hd_net;
 typedef const float *(*hd_weight_fn)(void *user, const char *tf_name, long long *numel);
 void hd_net_destroy(hd_net *net);
