@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -113,3 +115,18 @@ def test_host_logic_without_gpu():
     th, tl = tf32_split(w)
     assert np.all((th.view(np.uint32) & 0x1FFF) == 0) and np.all((tl.view(np.uint32) & 0x1FFF) == 0)
     assert np.abs(th.astype(np.float64) + tl.astype(np.float64) - w).max() < 2.0 ** -21 * np.abs(w).max()
+
+def test_plain_c_consumer(tmp_path):
+    """tests/c/consumer.c: gcc -std=c99 against include/hd_b200.h, dlopen of the shipped library, a network-level create call whose
+    weight callback has nothing to offer -> HD_ERR_INVALID naming the first variable it asked for (no device touched)."""
+    import shutil
+    import subprocess
+    from human_dynamics_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    exe = str(tmp_path / 'consumer')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-D_DEFAULT_SOURCE', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'tests', 'c', 'consumer.c'), '-o', exe, '-ldl'])
+    r = subprocess.run([exe, _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    assert 'rc=1' in r.stdout and 'resnet_v2_50/conv1/weights' in r.stdout and 'asked=1' in r.stdout
