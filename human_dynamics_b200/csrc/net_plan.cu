@@ -259,6 +259,8 @@ int bind_fmovie(hd_net *net, const float *x, float *out) {
   Builder b{net};
   net->steps.clear();
   net->maps.clear();
+  net->bound_in = nullptr;             // a failure below must not leave a half-built plan looking bound
+  net->bound_out = nullptr;
   const int B = net->B, T = net->T, C = net->C, L = net->layers;
   // persist layout: [0] act.hi [1] act.lo [2] mid [3] buf0 [4] buf1, then per block: gn1 gamma, gn1 beta, gn2 gamma, gn2 beta
   Pair act{net->persist[0], net->persist[1]};
@@ -275,18 +277,19 @@ int bind_fmovie(hd_net *net, const float *x, float *out) {
     hd_conv_desc d;
     Builder::Bind bd;
     bd.n = B; bd.H = T; bd.W = 1; bd.in = act; bd.out = mid;
-    if (!b.bind(convs[2 * i], bd, d)) return b.rc;
+    if (!b.bind(convs[2 * i], bd, d)) { net->steps.clear(); return b.rc; }
     b.conv_step(d);
     net->steps.push_back([=](cudaStream_t st) { return hd_groupnorm_relu_split(mid, g2, b2, act.hi, act.lo, B, T, C, 32, 1e-6f, (void *)st); });
     Builder::Bind be;
     be.n = B; be.H = T; be.W = 1; be.in = act; be.out = o; be.res = cur; be.res_ld = C; be.res_H = T; be.res_W = 1; be.res_stride = 1;
-    if (!b.bind(convs[2 * i + 1], be, d)) return b.rc;
+    if (!b.bind(convs[2 * i + 1], be, d)) { net->steps.clear(); return b.rc; }
     b.conv_step(d);
     cur = o;
   }
+  if (b.rc != HD_OK) { net->steps.clear(); return b.rc; }
   net->bound_in = x;
   net->bound_out = out;
-  return b.rc;
+  return HD_OK;
 }
 
 }  // namespace
