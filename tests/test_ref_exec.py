@@ -247,6 +247,51 @@ np.savez(sys.argv[2], **out)
                 assert np.array_equal(a, b), k
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
+@pytest.mark.timeout(600)
+def test_process_image_random_sweep_against_the_reference_tree(tmp_path):
+    """40 random (frame size, bbox) cases through the reference's own process_image (run_video.py:56-107, imported from
+    /root/reference in a fresh interpreter, frames handed over as PNG files) vs the oracle (every pixel) and vs the host bookkeeping
+    the CUDA path uses (human_dynamics_b200.preprocess.crop_geometry: centre / start point / shape must be equal integers)."""
+    code = r'''
+import importlib.util, os, sys, numpy as np
+spec = importlib.util.spec_from_file_location('g', sys.argv[1]); g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+g.setup_paths()
+import cv2
+from src.evaluation.run_video import process_image
+rng = np.random.RandomState(314)
+out = {}
+for i in range(40):
+    H, W = int(rng.randint(60, 400)), int(rng.randint(60, 400))
+    s = float(rng.uniform(0.4, 1.8)); cx, cy = float(rng.uniform(0, W)), float(rng.uniform(0, H))
+    frame = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    path = os.path.join(sys.argv[2], 'f%d.png' % i)
+    cv2.imwrite(path, cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
+    r = process_image(path, np.array([cx, cy, s], np.float64))
+    out['case_%d' % i] = np.array([H, W, cx, cy, s], np.float64)
+    out['frame_%d' % i] = frame
+    out['img_%d' % i] = np.asarray(r['image'], np.float64)
+    out['meta_%d' % i] = np.array(list(r['center']) + list(r['start_pt']) + list(r['im_shape']), np.int64)
+np.savez(os.path.join(sys.argv[2], 'sweep.npz'), **out)
+'''
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    subprocess.check_call([sys.executable, '-W', 'ignore', '-c', code, os.path.join(HERE, 'golden', 'make_ref_exec_golden.py'), str(tmp_path)],
+                          cwd=str(tmp_path), env=env)
+    from oracle import preproc_ref
+    from human_dynamics_b200.preprocess import crop_geometry
+    with np.load(str(tmp_path / 'sweep.npz')) as z:
+        for i in range(40):
+            H, W, cx, cy, s = z['case_%d' % i]
+            r = preproc_ref.process_image(z['frame_%d' % i], [cx, cy, s])
+            meta = np.array(list(r['center']) + list(r['start_pt']) + list(r['im_shape']), np.int64)
+            assert np.array_equal(meta, z['meta_%d' % i]), i
+            assert r['image'].shape == z['img_%d' % i].shape and np.abs(r['image'] - z['img_%d' % i]).max() < 1e-12, i
+            if list(z['meta_%d' % i][4:]) == [224, 224]:            # (ragged crops are refused by the static-shape CUDA path)
+                gm = crop_geometry((int(H), int(W)), [cx, cy, s])
+                assert list(gm['center']) + list(gm['start_pt']) + list(gm['im_shape']) == list(z['meta_%d' % i]), i
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # GPU: the CUDA path reproduces the reference-source vectors through the drop-in surface
 # ---------------------------------------------------------------------------------------------------------------------------
