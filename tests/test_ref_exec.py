@@ -249,6 +249,54 @@ np.savez(sys.argv[2], **out)
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
 @pytest.mark.timeout(600)
+def test_smpl_random_sweep_against_the_reference_tree(tmp_path, smpl_model_dense):
+    """48 random poses with LARGE rotations (theta ~ N(0, 1), beta ~ N(0, 2)) and the dense-skinning-weight 19-keypoint model through the
+    reference's own SMPL / batch_lbs source (fresh interpreter over the stand-in) vs the oracle -- beyond the 5 poses of the fixture."""
+    import pickle
+    import scipy.sparse as sp
+    dd = dict(smpl_model_dense)
+    dd['J_regressor'] = sp.csc_matrix(smpl_model_dense['J_regressor'])
+    dd['cocoplus_regressor'] = sp.csc_matrix(smpl_model_dense['cocoplus_regressor'])
+    with open(str(tmp_path / 'smpl.pkl'), 'wb') as f:
+        pickle.dump(dd, f, protocol=2)
+    rng = np.random.RandomState(2718)
+    beta = rng.normal(0, 2.0, size=(48, 10)).astype(np.float32)
+    theta = rng.normal(0, 1.0, size=(48, 72)).astype(np.float32)
+    theta[1, :3] = [np.pi, 0, 0]                                   # the mean pose's root rotation (tester.py:126-127)
+    cam = rng.normal(0, 1, size=(48, 3)).astype(np.float32)
+    np.savez(str(tmp_path / 'in.npz'), beta=beta, theta=theta, cam=cam)
+    code = r'''
+import importlib.util, sys, numpy as np
+spec = importlib.util.spec_from_file_location('g', sys.argv[1]); g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+g.setup_paths()
+import tensorflow as tf
+from src.tf_smpl.batch_smpl import SMPL
+from src.tf_smpl.projection import batch_orth_proj_idrot
+z = np.load(sys.argv[2] + '/in.npz')
+s = SMPL(sys.argv[2] + '/smpl.pkl')
+v, j, R = s(tf.constant(z['beta']), tf.constant(z['theta']), get_skin=True)
+k = batch_orth_proj_idrot(j, tf.constant(z['cam']))
+r = tf.Session().run({'verts': v, 'joints': j, 'Rs': R, 'Jtr': s.J_transformed, 'kps': k})
+np.savez(sys.argv[2] + '/out.npz', **r)
+'''
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    subprocess.check_call([sys.executable, '-W', 'ignore', '-c', code, os.path.join(HERE, 'golden', 'make_ref_exec_golden.py'), str(tmp_path)],
+                          cwd=str(tmp_path), env=env)
+    from oracle import smpl_ref
+    o = smpl_ref.SMPLRef(smpl_model_dense)
+    v, j, Rs = o(beta, theta, get_skin=True)
+    with np.load(str(tmp_path / 'out.npz')) as z:
+        assert z['joints'].shape == (48, 19, 3)
+        assert rel_err(v, z['verts']) < REL_ORACLE and rel_err(j, z['joints']) < REL_ORACLE and rel_err(Rs, z['Rs']) < REL_ORACLE
+        assert rel_err(o.J_transformed, z['Jtr']) < REL_ORACLE
+        assert rel_err(smpl_ref.batch_orth_proj_idrot(j, cam), z['kps']) < REL_ORACLE
+        v64 = smpl_ref.SMPLRef(smpl_model_dense, dtype=np.float64)(beta, theta, get_skin=True)[0]
+        assert rel_err(z['verts'], v64) < 1e-5                    # the reference's float32 graph itself is this close to float64 truth
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
+@pytest.mark.timeout(600)
 def test_process_image_random_sweep_against_the_reference_tree(tmp_path):
     """40 random (frame size, bbox) cases through the reference's own process_image (run_video.py:56-107, imported from
     /root/reference in a fresh interpreter, frames handed over as PNG files) vs the oracle (every pixel) and vs the host bookkeeping
