@@ -249,6 +249,50 @@ np.savez(sys.argv[2], **out)
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
 @pytest.mark.timeout(600)
+def test_models_other_configuration_against_the_reference_tree(tmp_path):
+    """A configuration the committed fixture does not hold -- num_conv_layers=2, B=3, T=7, delta heads (-3, +3), other weights (seed 31)
+    -- through the reference's own models.py (az_fc2_groupnorm, batch_pred_omega -> call_hmr_ief -> hmr_ief), executed live, vs the oracle."""
+    code = r'''
+import importlib.util, sys, numpy as np
+spec = importlib.util.spec_from_file_location('g', sys.argv[1]); g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+syn, _ = g.setup_paths()
+import tensorflow as tf
+from src import models
+w = syn.make_synthetic_weights(seed=31, num_conv_layers=2, delta_t_values=(-3, 3))
+rng = np.random.RandomState(32)
+x = rng.normal(0, 1, size=(3, 7, 2048)).astype(np.float32)
+y = models.get_temporal_encoder()(is_training=False, net=tf.constant(x), num_conv_layers=2)
+om0 = np.tile(np.asarray(w['mean_param'], np.float32).reshape(1, 85), (21, 1))
+om, deltas = models.batch_pred_omega(input_features=y, batch_size=3, is_training=False, num_output=85, omega_mean=tf.constant(om0),
+                                     sequence_length=7, scope='single_view_ief', predict_delta_keys=[3, 0, -3],
+                                     use_delta_from_pred=True, use_optcam=True)
+for v in tf.global_variables():
+    v.load(w[v.op_name])
+r = tf.Session().run({'strips': y, 'omega': om, 'd-3': deltas[-3], 'd3': deltas[3]})
+r['names'] = np.array(sorted(v.op_name for v in tf.global_variables()))
+np.savez(sys.argv[2] + '/out.npz', **r)
+'''
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    subprocess.check_call([sys.executable, '-W', 'ignore', '-c', code, os.path.join(HERE, 'golden', 'make_ref_exec_golden.py'), str(tmp_path)],
+                          cwd=str(tmp_path), env=env)
+    from human_dynamics_b200 import synthetic
+    from oracle import nets_ref
+    w = synthetic.make_synthetic_weights(seed=31, num_conv_layers=2, delta_t_values=(-3, 3))
+    x = np.random.RandomState(32).normal(0, 1, size=(3, 7, 2048)).astype(np.float32)
+    strips = nets_ref.az_fc2_groupnorm(torch.from_numpy(x), w, 2)
+    om0 = np.tile(np.asarray(w['mean_param'], np.float32).reshape(1, 85), (21, 1))
+    om, deltas = nets_ref.batch_pred_omega(strips, 3, w, 85, om0, 7, 'single_view_ief', [3, 0, -3], use_delta_from_pred=True, use_optcam=True)
+    with np.load(str(tmp_path / 'out.npz')) as z:
+        assert rel_err(strips.numpy(), z['strips']) < REL_ORACLE
+        assert rel_err(om.numpy(), z['omega']) < REL_ORACLE
+        assert rel_err(deltas[-3].numpy(), z['d-3']) < REL_ORACLE and rel_err(deltas[3].numpy(), z['d3']) < REL_ORACLE
+        names = set(str(n) for n in z['names'])
+        assert names == set(k for k in w if not k.startswith('resnet_v2_50/') and k != 'mean_param')      # scopes _past3 / _future3, 2 blocks
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
+@pytest.mark.timeout(600)
 def test_smpl_random_sweep_against_the_reference_tree(tmp_path, smpl_model_dense):
     """48 random poses with LARGE rotations (theta ~ N(0, 1), beta ~ N(0, 2)) and the dense-skinning-weight 19-keypoint model through the
     reference's own SMPL / batch_lbs source (fresh interpreter over the stand-in) vs the oracle -- beyond the 5 poses of the fixture."""
