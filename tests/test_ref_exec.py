@@ -247,6 +247,49 @@ np.savez(sys.argv[2], **out)
                 assert np.array_equal(a, b), k
 
 
+SLIDING_CASES = [(23, 2, 20, 3), (3, 1, 20, 3), (16, 2, 20, 3), (17, 2, 20, 3), (1, 4, 20, 3), (40, 1, 13, 3), (9, 3, 12, 2), (30, 2, 9, 2),
+                 (5, 2, 6, 1)]        # (N frames, B, T, num_conv_layers): ragged tails, N < one window, exact multiples, minimal T = fov
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
+@pytest.mark.timeout(600)
+def test_sliding_window_arithmetic_equals_the_reference_tree(tmp_path):
+    """tester.py:260-312 (margins, zero-frame padding, stride, which prediction is kept for which frame) executed from the reference
+    with `predict` replaced by a probe that returns the frame ids it was shown, vs the drop-in Tester's literal window path with the
+    same probe -- for window shapes the network-level fixture does not cover.  (The drop-in's cached-feature path is checked against its
+    literal path bit for bit on the GPU.)"""
+    code = r'''
+import importlib.util, sys, numpy as np
+spec = importlib.util.spec_from_file_location('g', sys.argv[1]); g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+g.setup_paths()
+from src.evaluation.tester import Tester
+out = {}
+for ci, (N, B, T, L) in enumerate(eval(sys.argv[3])):
+    t = Tester.__new__(Tester)
+    t.batch_size, t.sequence_length, t.img_size, t.fov = B, T, 2, L * 4 + 1
+    t.predict = lambda images: {'ids': np.asarray(images)[:, :, 0, 0, 0].copy(), 'two': np.asarray(images)[:, :, :, 0, 0] * 2.0}
+    frames = np.tile((np.arange(N, dtype=np.float64) + 1.0).reshape(N, 1, 1, 1), (1, 2, 2, 3))
+    r = t.predict_all_images(frames)
+    out['ids_%d' % ci], out['two_%d' % ci] = np.asarray(r['ids']), np.asarray(r['two'])
+np.savez(sys.argv[2] + '/out.npz', **out)
+'''
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    subprocess.check_call([sys.executable, '-W', 'ignore', '-c', code, os.path.join(HERE, 'golden', 'make_ref_exec_golden.py'), str(tmp_path),
+                           repr(SLIDING_CASES)], cwd=str(tmp_path), env=env)
+    from src.evaluation.tester import Tester
+    with np.load(str(tmp_path / 'out.npz')) as z:
+        for ci, (N, B, T, L) in enumerate(SLIDING_CASES):
+            t = Tester.__new__(Tester)
+            t.batch_size, t.sequence_length, t.img_size, t.fov = B, T, 2, L * 4 + 1
+            t.predict = lambda images, copy=True: {'ids': np.asarray(images)[:, :, 0, 0, 0].copy(), 'two': np.asarray(images)[:, :, :, 0, 0] * 2.0}
+            frames = np.tile((np.arange(N, dtype=np.float32) + 1.0).reshape(N, 1, 1, 1), (1, 2, 2, 3))
+            r = t.predict_all_images(frames, cache_features=False)
+            assert np.array_equal(r['ids'], z['ids_%d' % ci]), (N, B, T, L)
+            assert np.array_equal(r['two'], z['two_%d' % ci]), (N, B, T, L)
+            assert np.array_equal(z['ids_%d' % ci], np.arange(N) + 1.0)           # every frame is predicted from a window that saw it at full fov
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
 @pytest.mark.timeout(600)
 def test_models_other_configuration_against_the_reference_tree(tmp_path):
