@@ -68,3 +68,39 @@ def test_stage_plans_keep_the_pairs_inside_a_stage(fake_device):
     last_a = _convs(pa)[-1].d
     assert not last_a.out and last_a.out_hi and last_a.post2_relu == 1
     assert (pb.in_hw, pb.in_depth) == (pa.out_hw, pa.out_depth) == (4, 512)
+
+
+def test_fmovie_and_ief_plan_wiring(fake_device):
+    """f_movie fast path: per block GN+ReLU+split -> conv (k=3 over T, pad 1) -> GN+ReLU+split -> conv + residual; IEF fast path: phi split
+    once, per head one hoisted phi.W1 GEMM, per stage fc1-theta / fc2 (tensor cores) / fc3; delta heads write into the [N, D, 85] stack."""
+    nets = fake_device
+    from human_dynamics_b200 import synthetic
+    w = synthetic.make_synthetic_weights(seed=1)
+    B, T = 2, 20
+    fm = nets.FMoviePlan(nets.PackedFMovie(w, 'cpu', 3, tc='auto'), B, T, 'auto')
+    x = torch.zeros((B, T, 2048))
+    fm._bind(x)
+    assert [s[0] for s in fm.steps] == ['gns', 'conv'] * 6 and fm.num_launches == 12
+    convs = [s[1].d for s in fm.steps if s[0] == 'conv']
+    for i, d in enumerate(convs):
+        assert (d.n_img, d.H, d.W, d.KH, d.KW, d.pad_t, d.pad_l, d.Ho, d.Wo, d.Cin, d.Cout) == (B, T, 1, 3, 1, 1, 0, T, 1, 2048, 2048)
+        assert d.in_hi == fm.act[0].data_ptr() and d.impl == 3 and d.post_shift and not d.post_relu
+        assert bool(d.res) == (i % 2 == 1)                                   # the block's second conv adds the block input
+    assert convs[1].res == x.data_ptr() and convs[3].res == convs[1].out and convs[5].res == convs[3].out
+    assert fm.out.data_ptr() == convs[5].out
+
+    N = B * T
+    ief = nets.IEFPlan(nets.PackedIEF(w, 'cpu', tc='auto'), N, 3, None, 'auto')
+    assert ief.fast and ief.delta_keys == [-5, 5] and ief.num_launches == 33
+    phi, theta0 = torch.zeros((N, 2048)), torch.zeros((N, 85))
+    ief._bind(phi, theta0)
+    kinds = [op[0] for op in ief.main_ops]
+    assert kinds == ['conv'] + ['fc1t', 'conv', 'fc3'] * 3
+    # stage 0 starts from theta0, later stages from the running theta; the delta heads run in place on columns 3:75 of their slot
+    assert ief.main_ops[1][1].data_ptr() == theta0.data_ptr() and ief.main_ops[4][1].data_ptr() == ief.theta.data_ptr()
+    for i, dt in enumerate(ief.delta_keys):
+        ops = ief.delta_ops[dt]
+        view = ops[1][1]
+        assert view.data_ptr() == ief.delta_all.data_ptr() + (i * 85 + 3) * 4 and ops[1][2] == 2 * 85 and ops[3][4] == 2 * 85
+        assert ops[3][5].d == 72
+    assert ief.main_ops[3][5].d == 85
