@@ -267,10 +267,13 @@ def load_checkpoint(prefix, names=None, skip=None, verify_data=False):
             if names is not None:
                 raise ValueError('%s has unsupported dtype enum %d' % (name, e.dtype))
             continue                                 # strings etc. (e.g. object-graph metadata)
-        if e.shard_id not in shards:
-            path = '%s.data-%05d-of-%05d' % (prefix, e.shard_id, num_shards)
-            shards[e.shard_id] = np.memmap(path, dtype=np.uint8, mode='r')
-        raw = shards[e.shard_id][e.offset:e.offset + e.size]
+        if e.size == 0:                              # zero-size tensor: nothing to read (its shard may even be an empty file)
+            raw = np.zeros(0, np.uint8)
+        else:
+            if e.shard_id not in shards:
+                path = '%s.data-%05d-of-%05d' % (prefix, e.shard_id, num_shards)
+                shards[e.shard_id] = np.memmap(path, dtype=np.uint8, mode='r')
+            raw = shards[e.shard_id][e.offset:e.offset + e.size]
         count = int(np.prod(e.shape)) if e.shape else 1
         if raw.size != e.size or count * np.dtype(dt).itemsize != e.size:
             raise ValueError('%s: entry size %d does not match shape %s / data file' % (name, e.size, e.shape))
@@ -322,7 +325,7 @@ def save_checkpoint(prefix, tensors, block_size=4096):
     records, offset = [], 0
     with open(data_path, 'wb') as f:
         for n in names:
-            a = np.ascontiguousarray(tensors[n])
+            a = np.asarray(tensors[n], order='C')          # (np.ascontiguousarray would turn a scalar into shape (1,))
             if a.dtype not in _DTYPE_IDS:
                 raise ValueError('%s: dtype %s not supported' % (n, a.dtype))
             raw = a.astype(a.dtype.newbyteorder('<')).tobytes()

@@ -168,3 +168,36 @@ def test_smpl_faces_fixture_is_bit_exact():
     f = np.load(path)
     assert f.shape == (13776, 3) and f.dtype == np.uint32 and f.min() == 0 and f.max() == 6889
     assert len(np.unique(f)) == 6890
+
+
+def test_checkpoint_roundtrip_property_based(tmp_path):
+    """hypothesis: random variable sets (shared name prefixes, scalars, empty tensors, mixed dtypes) x random block sizes / restart
+    points through writer -> reader: every tensor comes back bit for bit, CRCs verify, index entries match."""
+    hyp = __import__('pytest').importorskip('hypothesis')
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from human_dynamics_b200 import tf_checkpoint
+    seg = st.sampled_from(['resnet_v2_50', 'block1', 'unit_1', 'bottleneck_v2', 'conv1', 'BatchNorm', 'weights', 'biases', 'gamma', 'a', 'aa',
+                           'single_view_ief_past5', '3D_module', 'fc1', 'w', 'x' * 40])
+    name = st.lists(seg, min_size=1, max_size=5).map('/'.join)
+    dtype = st.sampled_from([np.float32, np.float64, np.int32, np.int64, np.float16, np.uint8])
+    shape = st.lists(st.integers(0, 5), min_size=0, max_size=4).map(tuple)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(st.dictionaries(name, st.tuples(dtype, shape, st.integers(0, 2 ** 31 - 1)), min_size=1, max_size=25), st.integers(16, 600))
+    def check(spec, block_size):
+        tensors = {}
+        for n, (dt, shp, seed) in spec.items():
+            r = np.random.RandomState(seed)
+            tensors[n] = (r.normal(size=shp) * 100).astype(dt) if shp else np.asarray(r.normal() * 100).astype(dt)
+        counter[0] += 1
+        prefix = str(tmp_path / ('ck%d' % counter[0]))
+        tf_checkpoint.save_checkpoint(prefix, tensors, block_size=block_size)
+        nshards, entries = tf_checkpoint.read_index(prefix + '.index', verify=True)
+        assert nshards == 1 and set(entries) == set(tensors)
+        got = tf_checkpoint.load_checkpoint(prefix, names=list(tensors), verify_data=True)
+        assert set(got) == set(tensors)
+        for k, v in tensors.items():
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+
+    check()
