@@ -95,3 +95,26 @@ def test_run_video_process_image_surface():
     assert np.abs(got['image'] - ref['image']).max() < 2e-6
     assert list(got['center']) == list(ref['center']) and list(got['start_pt']) == list(ref['start_pt'])
     assert got['im_shape'] == ref['im_shape'] and got['scale'] == ref['scale']
+
+
+def test_geometry_table_equals_per_frame_crop_geometry():
+    """The vectorised host table hd_process_image consumes ({Hs, Ws, x0, y0} per frame, engine.predict_host / predict_frames) against the
+    per-frame bookkeeping that is itself checked against the reference's process_image (same float64 formulas -> same integers)."""
+    from human_dynamics_b200.preprocess import crop_geometry, geometry_table
+    rng = np.random.RandomState(5)
+    for _ in range(50):
+        H, W = int(rng.randint(60, 500)), int(rng.randint(60, 500))
+        n = int(rng.randint(1, 9))
+        boxes = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n), rng.uniform(0.3, 2.0, n)], axis=1)
+        boxes[0] = [W / 2.0, H / 2.0, 1.0]
+        boxes[-1, :2] = np.round(boxes[-1, :2]) + 0.5                      # exact .5 centres: np.round's half-to-even on both sides
+        table, infos = geometry_table((H, W), boxes, with_infos=True)
+        assert table.dtype == np.int32 and table.shape == (n, 4) and len(infos) == n
+        for i in range(n):
+            g = crop_geometry((H, W), boxes[i])
+            assert list(table[i]) == [g['new_size'][0], g['new_size'][1], g['origin'][0], g['origin'][1]], (H, W, boxes[i])
+            assert list(infos[i]['start_pt']) == list(g['start_pt']) and list(infos[i]['center']) == list(g['center'])
+    with pytest.raises(ValueError):
+        geometry_table((100, 100), [[50.0, 50.0, 1.0], [900.0, 50.0, 1.0]])   # one frame of the track is out of reach
+    with pytest.raises(ValueError):
+        geometry_table((100, 100), [[50.0, 50.0, 0.001]])                      # scale leaves an empty image
