@@ -104,3 +104,54 @@ def test_fmovie_and_ief_plan_wiring(fake_device):
         assert view.data_ptr() == ief.delta_all.data_ptr() + (i * 85 + 3) * 4 and ops[1][2] == 2 * 85 and ops[3][4] == 2 * 85
         assert ops[3][5].d == 72
     assert ief.main_ops[3][5].d == 85
+
+
+@pytest.mark.parametrize('dense', [False, True])
+def test_smpl_constant_packing_is_exact(smpl_model, smpl_model_dense, dense):
+    """SMPLConstants (the device layout of the SMPL pickle, built here on the CPU without the tensor-core packing): the integer tables
+    -- kinematic parents, ELL joint ids of the skinning weights, CSC vertex ids of the keypoint regressor -- and the weights they carry
+    reproduce the pickle's dense matrices exactly; the pre-composed joint regressor equals batch_smpl.py:110-118 evaluated in float64."""
+    from human_dynamics_b200.smpl import SMPLConstants
+    m = smpl_model_dense if dense else smpl_model
+    c = SMPLConstants(m, device='cpu', tc=False)
+    V = m['v_template'].shape[0]
+    assert c.num_verts == V == 6890 and c.num_kps == m['cocoplus_regressor'].shape[0]
+    # kintree_table[0] is stored as uint32 with 4294967295 for the root; batch_smpl.py:66 casts with astype(np.int32) -> -1
+    assert m['kintree_table'].dtype == np.uint32 and int(m['kintree_table'][0, 0]) == 4294967295
+    assert c.parents.dtype == np.int32 and c.parents.tolist() == [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+    assert [c.c.parents[i] for i in range(24)] == c.parents.tolist()
+    # ELL skinning weights -> dense (V, 24)
+    W = np.asarray(m['weights'], np.float64)
+    idx, w = c.lbs_idx.numpy(), c.lbs_w.numpy()
+    assert idx.shape == w.shape == (V, c.lbs_nnz) and c.lbs_nnz == (24 if dense else 4) and idx.dtype == np.int32
+    rec = np.zeros((V, 24), np.float32)
+    np.add.at(rec, (np.repeat(np.arange(V), c.lbs_nnz), idx.reshape(-1)), w.reshape(-1))
+    assert np.array_equal(rec, W.astype(np.float32))
+    nz = w != 0
+    assert np.all(idx[~nz] == 0)                                               # padding entries: joint 0 with weight 0
+    for v in (0, 17, V - 1):
+        assert list(idx[v][nz[v]]) == sorted(idx[v][nz[v]])                    # fixed (ascending joint) summation order
+    # CSC keypoint regressor -> dense (K, V)
+    K = c.num_kps
+    ptr, vid, kw = c.kp_ptr.numpy(), c.kp_vidx.numpy(), c.kp_w.numpy()
+    assert ptr[0] == 0 and np.all(np.diff(ptr) > 0) and ptr[-1] == len(vid) == len(kw) == c.c.kp_nnz_total
+    rec = np.zeros((K, V), np.float32)
+    for k in range(K):
+        rec[k, vid[ptr[k]:ptr[k + 1]]] = kw[ptr[k]:ptr[k + 1]]
+        assert np.all(np.diff(vid[ptr[k]:ptr[k + 1]]) > 0)
+    assert np.array_equal(rec, np.asarray(m['cocoplus_regressor'], np.float32))
+    lsp = SMPLConstants(m, joint_type='lsp', device='cpu', tc=False)
+    assert lsp.num_kps == 14 and lsp.c.kp_nnz_total == int(ptr[14])          # batch_smpl.py:81-82: the first 14 columns
+    with pytest.raises(ValueError):
+        SMPLConstants(m, joint_type='coco', device='cpu', tc=False)           # the reference prints 'BAD!!' and drops into ipdb
+    # blend basis rows: 10 shape rows then 207 pose rows, flattened like batch_smpl.py:45-48,60-63
+    dirs = c.dirs.numpy()
+    assert dirs.shape == (217, V * 3)
+    assert np.array_equal(dirs[:10], np.reshape(m['shapedirs'], [-1, 10]).T.astype(np.float32))
+    assert np.array_equal(dirs[10:], np.reshape(m['posedirs'], [-1, 207]).T.astype(np.float32))
+    # J(beta) = (beta . shapedirs + v_template) . J_regressor, pre-composed
+    beta = np.random.RandomState(0).normal(0, 2, size=(5, 10))
+    v_shaped = (beta @ np.reshape(m['shapedirs'], [-1, 10]).T).reshape(5, V, 3) + m['v_template']
+    J_ref = np.stack([v_shaped[:, :, k] @ np.asarray(m['J_regressor']).T for k in range(3)], axis=2)
+    J = c.J_template.numpy().astype(np.float64).reshape(1, 24, 3) + (beta @ c.J_shapedirs.numpy().astype(np.float64)).reshape(5, 24, 3)
+    assert np.abs(J - J_ref).max() < 1e-6
