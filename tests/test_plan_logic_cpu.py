@@ -155,3 +155,38 @@ def test_smpl_constant_packing_is_exact(smpl_model, smpl_model_dense, dense):
     J_ref = np.stack([v_shaped[:, :, k] @ np.asarray(m['J_regressor']).T for k in range(3)], axis=2)
     J = c.J_template.numpy().astype(np.float64).reshape(1, 24, 3) + (beta @ c.J_shapedirs.numpy().astype(np.float64)).reshape(5, 24, 3)
     assert np.abs(J - J_ref).max() < 1e-6
+
+
+def test_weight_packing_layouts_and_split_precision(fake_device):
+    """What the tensor-core kernels are fed: K-major [Cout_pad, K] with K = (ky, kx, ci) (TF HWIO flattened), each weight as an fp16
+    head + 2^11-scaled fp16 remainder that together carry >= 21 significant bits; conv1's 7x7x3 filter re-laid as 8 x 8 x 4 taps with
+    zero weights on the padding taps; BatchNorm folded in float64."""
+    nets = fake_device
+    rng = np.random.RandomState(3)
+    w = (rng.normal(0, 1, size=(3, 3, 64, 96)) / 24).astype(np.float32)
+    pc = nets.PackedConv(w, 'cpu', tc='auto')
+    assert pc.tc == 'f16' and (pc.K, pc.K_pad, pc.Cout) == (576, 576, 96)
+    hi, lo = pc.w_nk_hi.numpy(), pc.w_nk_lo.numpy()
+    assert hi.shape == lo.shape == (128, 576) and hi.dtype == lo.dtype == np.float16          # rows padded to the 128-wide N tile
+    assert not hi[96:].any() and not lo[96:].any()
+    rec = hi[:96].astype(np.float64) + lo[:96].astype(np.float64) / 2048.0
+    ref = w.reshape(576, 96).T.astype(np.float64)                                            # [co, (ky, kx, ci)]
+    assert np.abs(rec - ref).max() <= np.abs(ref).max() * 2.0 ** -21
+    assert np.array_equal(hi[:96], ref.astype(np.float16))                                   # head = RN_f16(w)
+    assert np.array_equal(pc.w_kn.numpy(), w.reshape(576, 96))                               # exact-FP32 path keeps TF's [K, Cout]
+    small = nets.PackedConv(w[:, :, :, :64], 'cpu', tc='auto')
+    assert small.w_nk_hi.shape == (64, 576)                                                  # Cout <= 64: 64-wide tile, no padding rows
+    # conv1 planes
+    w1 = rng.normal(0, 0.1, size=(7, 7, 3, 64)).astype(np.float32)
+    p1 = nets.PackedConv1Planes(w1, np.zeros(64, np.float32), 'cpu')
+    t = (p1.w_nk_hi.numpy().astype(np.float64) + p1.w_nk_lo.numpy().astype(np.float64) / 2048.0).reshape(64, 8, 8, 4)
+    assert not t[:, 7].any() and not t[:, :, 7].any() and not t[:, :, :, 3].any()            # phantom kernel row / pixel / channel
+    assert np.abs(t[:, :7, :7, :3] - w1.transpose(3, 0, 1, 2)).max() <= np.abs(w1).max() * 2.0 ** -21
+    assert p1.plane_width(224) == 232 and p1.plane_width(64) == 72
+    # fold_bn in float64
+    wd = {'p/gamma': rng.uniform(0.5, 1.5, 8).astype(np.float32), 'p/beta': rng.normal(size=8).astype(np.float32),
+          'p/moving_mean': rng.normal(size=8).astype(np.float32), 'p/moving_variance': rng.uniform(0.5, 1.5, 8).astype(np.float32)}
+    s, b = nets.fold_bn(wd, 'p')
+    x = rng.normal(size=(5, 8))
+    ref = wd['p/gamma'] * (x - wd['p/moving_mean']) / np.sqrt(wd['p/moving_variance'].astype(np.float64) + 1e-5) + wd['p/beta']
+    assert s.dtype == b.dtype == np.float32 and np.abs(x * s + b - ref).max() < 1e-6
