@@ -247,6 +247,52 @@ np.savez(sys.argv[2], **out)
                 assert np.array_equal(a, b), k
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree only exists in the build container')
+@pytest.mark.timeout(600)
+def test_eval_metrics_random_sweep_against_the_reference_tree(tmp_path):
+    """24 random cases (incl. mirrored point sets, where the similarity transform needs the reflection fix, and sparse visibility) through
+    the reference's own eval_util.py vs the drop-in src/evaluation/eval_util.py."""
+    code = r'''
+import importlib.util, sys, numpy as np
+spec = importlib.util.spec_from_file_location('g', sys.argv[1]); g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+g.setup_paths()
+from src.evaluation import eval_util as E
+rng = np.random.RandomState(99)
+out = {}
+for i in range(24):
+    gt = rng.normal(0, 0.4, size=(12, 14, 3)); pr = gt + rng.normal(0, 0.05, size=gt.shape)
+    if i % 3 == 0: pr[..., 0] *= -1.0                     # mirrored prediction
+    vis = rng.rand(12) > (0.6 if i % 4 == 0 else 0.1)
+    kg = np.concatenate([rng.rand(5, 19, 2) * 2 - 1, (rng.rand(5, 19, 1) > (0.75 if i % 5 == 0 else 0.2)).astype(np.float64)], axis=2)
+    kp = kg[:, :, :2] + rng.normal(0, 0.05, size=(5, 19, 2))
+    out['gt_%d' % i], out['pr_%d' % i], out['vis_%d' % i], out['kg_%d' % i], out['kp_%d' % i] = gt, pr, vis, kg, kp
+    e, pa = E.compute_error_3d(gt, pr)
+    out['e_%d' % i], out['pa_%d' % i] = np.asarray(e), np.asarray(pa)
+    out['sim_%d' % i] = E.compute_similarity_transform(pr[0], gt[0])
+    out['acc_%d' % i] = np.asarray(E.compute_error_accel(gt, pr, vis))
+    ek, epa, pck = E.compute_error_kp(kg, kp)
+    out['ek_%d' % i], out['epa_%d' % i], out['pck_%d' % i] = np.asarray(ek, np.float64), np.asarray(epa, np.float64), np.asarray(pck, np.float64)
+    out['ev_%d' % i] = np.asarray(E.compute_error_verts(gt, pr))
+np.savez(sys.argv[2] + '/out.npz', **out)
+'''
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    subprocess.check_call([sys.executable, '-W', 'ignore', '-c', code, os.path.join(HERE, 'golden', 'make_ref_exec_golden.py'), str(tmp_path)],
+                          cwd=str(tmp_path), env=env)
+    import src.evaluation.eval_util as E
+    with np.load(str(tmp_path / 'out.npz')) as z:
+        for i in range(24):
+            gt, pr, vis, kg, kp = (z['%s_%d' % (k, i)] for k in ('gt', 'pr', 'vis', 'kg', 'kp'))
+            e, pa = E.compute_error_3d(gt, pr)
+            assert np.allclose(e, z['e_%d' % i], rtol=1e-9) and np.allclose(pa, z['pa_%d' % i], rtol=1e-6, atol=1e-9), i
+            assert np.allclose(E.compute_similarity_transform(pr[0], gt[0]), z['sim_%d' % i], atol=1e-8), i
+            assert np.allclose(E.compute_error_accel(gt, pr, vis), z['acc_%d' % i], rtol=1e-9, atol=1e-12), i
+            ek, epa, pck = E.compute_error_kp(kg, kp)
+            for a, b in ((ek, z['ek_%d' % i]), (epa, z['epa_%d' % i]), (pck, z['pck_%d' % i])):
+                assert np.allclose(np.asarray(a, np.float64), b, rtol=1e-8, atol=1e-10, equal_nan=True), i
+            assert np.allclose(E.compute_error_verts(gt, pr), z['ev_%d' % i], rtol=1e-9), i
+
+
 SLIDING_CASES = [(23, 2, 20, 3), (3, 1, 20, 3), (16, 2, 20, 3), (17, 2, 20, 3), (1, 4, 20, 3), (40, 1, 13, 3), (9, 3, 12, 2), (30, 2, 9, 2),
                  (5, 2, 6, 1)]        # (N frames, B, T, num_conv_layers): ragged tails, N < one window, exact multiples, minimal T = fov
 
