@@ -89,6 +89,8 @@ SIGNATURES = {
     'hd_fmovie_forward': (_i, [_vp, _vp, _vp, _vp]),
     'hd_ief_create': (_i, [_vp, _vp, _i, C.POINTER(_i), _i, C.POINTER(_vp)]),
     'hd_ief_forward': (_i, [_vp, _vp, _vp, _vp, _vp]),
+    'hd_smpl_pack_sizes': (_i, [_i, _i, _vp, _vp, C.POINTER(_i), C.POINTER(_i)]),
+    'hd_smpl_pack': (_i, [_i, _i] + [_vp] * 13 + [_i] + [_vp] * 4),
     'hd_smpl_workspace_bytes': (_sz, [_i]),
     'hd_smpl_forward': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'hd_smpl_pose': (_i, [C.POINTER(SmplConsts), _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),

@@ -213,6 +213,19 @@ typedef struct {
   int parents[24];             /* kintree_table[0] as int32 (root -1), batch_smpl.py:66 */
 } hd_smpl_consts;
 
+/* Host-side packing of the SMPL model (the contents of the official pickle as dense float64 arrays) into the arrays hd_smpl_consts points
+ * at -- what SMPL.__init__ does in the reference (batch_smpl.py:27-86) plus the layouts the kernels want.  Pure host code, no CUDA call:
+ * the caller uploads the outputs and stores the device pointers in hd_smpl_consts.  All pointers are HOST memory.
+ *   in : v_template [V,3], shapedirs [V,3,10], posedirs [V,3,207], J_regressor [24,V], weights [V,24], kp_regressor [K,V] (cocoplus_regressor,
+ *        or its first 14 rows for joint_type 'lsp', batch_smpl.py:81-82), kintree_parents = kintree_table[0] as stored (uint32, root 4294967295)
+ *   out: v_template_out [V*3] f32, dirs [217, V*3] f32, J_template [72] f32, J_shapedirs [10,72] f32, lbs_idx / lbs_w [V, lbs_nnz] (ELL: joint
+ *        ids ascending, padding = joint 0 with weight 0), kp_ptr [K+1] / kp_vidx / kp_w [kp_nnz_total] (CSC over keypoints), parents int[24]
+ * hd_smpl_pack_sizes reports lbs_nnz (4, or the per-vertex maximum rounded up to a multiple of 4, at most 24) and kp_nnz_total first. */
+int hd_smpl_pack_sizes(int V, int K, const double *weights, const double *kp_regressor, int *lbs_nnz, int *kp_nnz_total);
+int hd_smpl_pack(int V, int K, const double *v_template, const double *shapedirs, const double *posedirs, const double *J_regressor,
+                 const double *weights, const double *kp_regressor, const unsigned int *kintree_parents, float *v_template_out, float *dirs,
+                 float *J_template, float *J_shapedirs, int *lbs_idx, float *lbs_w, int lbs_nnz, int *kp_ptr, int *kp_vidx, float *kp_w,
+                 int *parents);
 size_t hd_smpl_workspace_bytes(int N);
 /* beta rows of 10 at stride beta_ld, theta rows of 72 at stride theta_ld, cam rows of 3 at stride cam_ld (so the
  * three can alias columns [75:85], [3:75], [0:3] of one [N,85] omega buffer, src/omega.py:231-235).

@@ -190,3 +190,41 @@ def test_weight_packing_layouts_and_split_precision(fake_device):
     x = rng.normal(size=(5, 8))
     ref = wd['p/gamma'] * (x - wd['p/moving_mean']) / np.sqrt(wd['p/moving_variance'].astype(np.float64) + 1e-5) + wd['p/beta']
     assert s.dtype == b.dtype == np.float32 and np.abs(x * s + b - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize('dense,lsp', [(False, False), (True, False), (False, True)])
+def test_c_smpl_pack_equals_python_packing(smpl_model, smpl_model_dense, dense, lsp):
+    """hd_smpl_pack (csrc/smpl_pack.cu, host-only C: what a C consumer calls to fill hd_smpl_consts) against the Python packing of
+    SMPLConstants: integer tables and plain casts bit for bit, the pre-composed joint regressor to float32 rounding."""
+    import ctypes as C
+    from human_dynamics_b200 import _lib
+    from human_dynamics_b200.smpl import SMPLConstants
+    m = smpl_model_dense if dense else smpl_model
+    ref = SMPLConstants(m, joint_type='lsp' if lsp else 'cocoplus', device='cpu', tc=False)
+    V = m['v_template'].shape[0]
+    kreg = np.ascontiguousarray(np.asarray(m['cocoplus_regressor'], np.float64)[:14] if lsp else np.asarray(m['cocoplus_regressor'], np.float64))
+    K = kreg.shape[0]
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)              # noqa: E731
+    vt, sd, pd, jr, w = f64(m['v_template']), f64(m['shapedirs']), f64(m['posedirs']), f64(m['J_regressor']), f64(m['weights'])
+    kin = np.ascontiguousarray(m['kintree_table'][0], np.uint32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)                     # noqa: E731
+    nnz, tot = C.c_int(), C.c_int()
+    assert _lib.lib.hd_smpl_pack_sizes(V, K, ptr(w), ptr(kreg), C.byref(nnz), C.byref(tot)) == 0
+    assert (nnz.value, tot.value) == (ref.lbs_nnz, ref.c.kp_nnz_total)
+    out = {'vt': np.empty(V * 3, np.float32), 'dirs': np.empty((217, V * 3), np.float32), 'Jt': np.empty(72, np.float32),
+           'Js': np.empty((10, 72), np.float32), 'idx': np.empty((V, nnz.value), np.int32), 'w': np.empty((V, nnz.value), np.float32),
+           'kp_ptr': np.empty(K + 1, np.int32), 'kp_vidx': np.empty(tot.value, np.int32), 'kp_w': np.empty(tot.value, np.float32),
+           'parents': np.empty(24, np.int32)}
+    rc = _lib.lib.hd_smpl_pack(V, K, ptr(vt), ptr(sd), ptr(pd), ptr(jr), ptr(w), ptr(kreg), ptr(kin), ptr(out['vt']), ptr(out['dirs']),
+                               ptr(out['Jt']), ptr(out['Js']), ptr(out['idx']), ptr(out['w']), nnz.value, ptr(out['kp_ptr']),
+                               ptr(out['kp_vidx']), ptr(out['kp_w']), ptr(out['parents']))
+    assert rc == 0, _lib.lib.hd_last_error()
+    assert np.array_equal(out['vt'], ref.v_template.numpy()) and np.array_equal(out['dirs'], ref.dirs.numpy())
+    assert np.array_equal(out['idx'], ref.lbs_idx.numpy()) and np.array_equal(out['w'], ref.lbs_w.numpy())
+    assert np.array_equal(out['kp_ptr'], ref.kp_ptr.numpy()) and np.array_equal(out['kp_vidx'], ref.kp_vidx.numpy())
+    assert np.array_equal(out['kp_w'], ref.kp_w.numpy()) and out['parents'].tolist() == ref.parents.tolist()
+    assert np.allclose(out['Jt'], ref.J_template.numpy(), rtol=3e-7, atol=1e-9)
+    assert np.allclose(out['Js'], ref.J_shapedirs.numpy(), rtol=3e-7, atol=1e-9)
+    assert _lib.lib.hd_smpl_pack(V, K, ptr(vt), ptr(sd), ptr(pd), ptr(jr), ptr(w), ptr(kreg), ptr(kin), ptr(out['vt']), ptr(out['dirs']),
+                                 ptr(out['Jt']), ptr(out['Js']), ptr(out['idx']), ptr(out['w']), nnz.value + 4, ptr(out['kp_ptr']),
+                                 ptr(out['kp_vidx']), ptr(out['kp_w']), ptr(out['parents'])) == 1       # wrong lbs_nnz: HD_ERR_INVALID
