@@ -74,6 +74,7 @@ SIGNATURES = {
     'hd_subsample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hd_bnrelu_avgpool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'hd_process_image': (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    'hd_crop_geometry': (_i, [_i, _i, _vp, _i, _vp, _vp, _vp]),
     'hd_groupnorm_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'hd_groupnorm_relu_split': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'hd_split_f16': (_i, [_vp, _vp, _vp, _ll, _vp]),

@@ -86,3 +86,28 @@ int hd_smpl_pack(int V, int K, const double *v_template, const double *shapedirs
 }
 
 }  // extern "C"
+
+// ---- host bookkeeping of process_image (src/evaluation/run_video.py:69-100 + resize_img, src/util/common.py:7-14): the {Hs, Ws, x0, y0}
+// row hd_process_image wants per frame, and the dict entries the reference returns.  Same float64 formulas as the reference's numpy code
+// (floor of shape * scale; np.round = round-half-to-even of centre * actual factor, with the reference's own x*fy / y*fx mix-up).
+#include <cmath>
+
+extern "C" int hd_crop_geometry(int H, int W, const double *bbox /* cx, cy, scale */, int img_size, int *geom /* Hs, Ws, x0, y0 */,
+                                int *center /* 2, nullable */, int *start_pt /* 2, nullable */) {
+  HD_REQUIRE(H > 0 && W > 0 && bbox && geom && img_size > 0 && img_size % 2 == 0, "hd_crop_geometry: bad arguments");
+  const double scale = bbox[2];
+  const long long hs = (long long)std::floor((double)H * scale), ws = (long long)std::floor((double)W * scale);
+  HD_REQUIRE(hs >= 1 && ws >= 1 && hs < (1ll << 30) && ws < (1ll << 30), "hd_crop_geometry: bbox scale leaves an empty (or absurd) image");
+  const double fy = (double)hs / (double)H, fx = (double)ws / (double)W;
+  // center_scaled = np.round(center * [fy, fx]).astype(int)   (run_video.py:75: x is scaled by the y factor and vice versa)
+  const long long cx = (long long)std::nearbyint(bbox[0] * fy) + img_size, cy = (long long)std::nearbyint(bbox[1] * fx) + img_size;
+  const long long sx = cx - img_size / 2, sy = cy - img_size / 2, ex = cx + img_size / 2, ey = cy + img_size / 2;
+  if (sx < 0 || sy < 0 || ex > ws + 2 * img_size || ey > hs + 2 * img_size) {
+    hd::set_last_error_text("hd_crop_geometry: bbox centre is more than one crop away from the frame (the reference yields a ragged crop)");
+    return HD_ERR_INVALID;
+  }
+  geom[0] = (int)hs; geom[1] = (int)ws; geom[2] = (int)(sx - img_size); geom[3] = (int)(sy - img_size);
+  if (center) { center[0] = (int)(cx - sx); center[1] = (int)(cy - sy); }
+  if (start_pt) { start_pt[0] = (int)sx; start_pt[1] = (int)sy; }
+  return HD_OK;
+}

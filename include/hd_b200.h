@@ -144,6 +144,11 @@ int hd_bnrelu_avgpool(const float *in, const float *scale, const float *shift, f
  * fp16 planes [N,S+6,WP,4] the tensor-core conv1 reads (hd_pack_conv1_planes layout; border cleared once by the caller). */
 int hd_process_image(const unsigned char *frames, int N, int H, int W, const int *geom, float *out, int S, void *plane_hi,
                      void *plane_lo, int WP, void *stream);
+/* Host bookkeeping of process_image for one frame (no CUDA call): bbox = {cx, cy, scale} as float64 -> geom = the {Hs, Ws, x0, y0} row
+ * hd_process_image takes, and optionally the reference's `center` (after the crop) and `start_pt` (in the edge-padded scaled image)
+ * (run_video.py:69-100; floor / round-half-to-even in double like the reference's numpy code).  HD_ERR_INVALID when the reference would
+ * return a crop smaller than img_size x img_size. */
+int hd_crop_geometry(int H, int W, const double *bbox, int img_size, int *geom, int *center, int *start_pt);
 
 /* ---- f_movie GroupNorm statistics (tf.contrib.layers.group_norm at src/models.py:155,188) ----
  * x [B,T,C]; per (clip, group) mean / biased variance over T*(C/groups) elements (two-pass);

@@ -118,3 +118,34 @@ def test_geometry_table_equals_per_frame_crop_geometry():
         geometry_table((100, 100), [[50.0, 50.0, 1.0], [900.0, 50.0, 1.0]])   # one frame of the track is out of reach
     with pytest.raises(ValueError):
         geometry_table((100, 100), [[50.0, 50.0, 0.001]])                      # scale leaves an empty image
+
+
+def test_c_crop_geometry_equals_python_bookkeeping():
+    """hd_crop_geometry (host-only C entry for consumers without Python) vs crop_geometry on random boxes incl. exact .5 products
+    (round-half-to-even) and the refused out-of-reach case."""
+    import ctypes as C
+    from human_dynamics_b200 import _lib
+    from human_dynamics_b200.preprocess import crop_geometry
+    rng = np.random.RandomState(11)
+    cases = [(rng.randint(60, 500), rng.randint(60, 500), rng.uniform(0, 500), rng.uniform(0, 500), rng.uniform(0.3, 2.0)) for _ in range(300)]
+    cases += [(200, 300, 100.5, 50.5, 1.0), (200, 300, 101.5, 51.5, 1.0), (100, 100, 0.5, 99.5, 2.0), (224, 224, 112.0, 112.0, 1.0)]
+    ok = 0
+    for H, W, cx, cy, s in cases:
+        H, W = int(H), int(W)
+        cx, cy = min(cx, W), min(cy, H)
+        bbox = np.array([cx, cy, s], np.float64)
+        geom, cen, sp = np.zeros(4, np.int32), np.zeros(2, np.int32), np.zeros(2, np.int32)
+        rc = _lib.lib.hd_crop_geometry(H, W, bbox.ctypes.data_as(C.c_void_p), 224, geom.ctypes.data_as(C.c_void_p),
+                                       cen.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p))
+        try:
+            g = crop_geometry((H, W), bbox)
+        except ValueError:
+            assert rc == 1
+            continue
+        assert rc == 0
+        ok += 1
+        assert geom.tolist() == [g['new_size'][0], g['new_size'][1], g['origin'][0], g['origin'][1]], (H, W, cx, cy, s)
+        assert cen.tolist() == list(g['center']) and sp.tolist() == list(g['start_pt'])
+    assert ok > 250
+    bbox = np.array([900.0, 50.0, 1.0])
+    assert _lib.lib.hd_crop_geometry(100, 100, bbox.ctypes.data_as(C.c_void_p), 224, geom.ctypes.data_as(C.c_void_p), None, None) == 1
