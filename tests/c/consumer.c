@@ -21,6 +21,7 @@ typedef const char *(*str_fn)(void);
 typedef const char *(*status_fn)(int);
 typedef int (*create_fn)(hd_weight_fn, void *, int, int, hd_net **);
 typedef void (*destroy_fn)(hd_net *);
+typedef int (*geom_fn)(int, int, const double *, int, int *, int *, int *);
 
 int main(int argc, char **argv) {
   if (argc < 2) return 2;
@@ -31,7 +32,16 @@ int main(int argc, char **argv) {
   status_fn status_string = (status_fn)dlsym(h, "hd_status_string");
   create_fn create = (create_fn)dlsym(h, "hd_resnet50_create");
   destroy_fn destroy = (destroy_fn)dlsym(h, "hd_net_destroy");
-  if (!version || !last_error || !status_string || !create || !destroy) return 4;
+  geom_fn crop_geometry = (geom_fn)dlsym(h, "hd_crop_geometry");
+  if (!version || !last_error || !status_string || !create || !destroy || !crop_geometry) return 4;
+  {
+    /* run_video.py:69-100 for a 240x320 frame, bbox centre (40.3, 200.7), scale 0.62 (case 1 of tests/golden/preproc_cases.py) */
+    const double bbox[3] = {40.3, 200.7, 0.62};
+    int geom[4], center[2], start[2];
+    int grc = crop_geometry(240, 320, bbox, 224, geom, center, start);
+    printf("geom rc=%d %d %d %d %d center=%d,%d start=%d,%d\n", grc, geom[0], geom[1], geom[2], geom[3], center[0], center[1], start[0], start[1]);
+    if (grc != HD_OK) return 5;
+  }
   hd_net *net = (hd_net *)0x1;
   hd_conv_desc d;
   memset(&d, 0, sizeof(d));

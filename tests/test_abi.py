@@ -130,3 +130,8 @@ def test_plain_c_consumer(tmp_path):
     r = subprocess.run([exe, _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout
     assert 'rc=1' in r.stdout and 'resnet_v2_50/conv1/weights' in r.stdout and 'asked=1' in r.stdout
+    from human_dynamics_b200.preprocess import crop_geometry
+    g = crop_geometry((240, 320), [40.3, 200.7, 0.62])
+    want = 'geom rc=0 %d %d %d %d center=%d,%d start=%d,%d' % (g['new_size'][0], g['new_size'][1], g['origin'][0], g['origin'][1],
+                                                             g['center'][0], g['center'][1], g['start_pt'][0], g['start_pt'][1])
+    assert want in r.stdout, (want, r.stdout)
